@@ -1,0 +1,62 @@
+// Internal C++ interfaces between the translation units of libevcplm.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace evc {
+
+// hamming.cu
+int64_t hamming_plane_words(int64_t N, int L);
+int64_t hamming_num_tiles(int64_t N);
+int hamming_pack(const uint8_t *d_codes, int64_t N, int L, uint32_t *d_planes, cudaStream_t st);
+int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_identical,
+                        int64_t tile_begin, int64_t tile_end, int *d_counts, cudaStream_t st);
+
+// plm_gather.cu -- geometry of the expanded coupling tensor and the gather-path kernels
+struct PlmGeom {
+    int64_t N;        // sequences on this handle
+    int L;            // sites
+    int Lp;           // L rounded up to 4 (bulk-copy alignment of a site's row block)
+    int q;            // model states (QA)
+    int QB;           // neighbour states incl. the ignored-gap row (q or q+1)
+    int S;            // row stride in floats (odd => conflict-free shared-memory gathers)
+    int gap_code;     // -1 or q
+    int64_t Nr;       // N rounded up to the backward tile (rows of the residual buffer)
+    int64_t Nld;      // leading dimension of the packed column-major MSA
+    int L4;           // ceil(L/4) packed site words
+    int ntiles_f;     // forward sequence tiles
+    int ntiles_b;     // backward sequence tiles
+    int64_t n_params;
+    __host__ __device__ int64_t blk() const { return (int64_t)QB * S; }                    // floats per (i,j) block
+    __host__ __device__ int64_t row_block() const { return (int64_t)Lp * blk(); }          // floats per site i
+    __host__ __device__ int64_t w_floats() const { return (int64_t)L * row_block(); }
+};
+
+constexpr int PLM_FWD_TS = 512;    // sequences per forward CTA (256 threads x 2)
+constexpr int PLM_BWD_TS = 2048;   // sequences per backward tile (residual tile in shared memory)
+
+bool plm_supported_q(int q);
+int plm_pack_msa(const PlmGeom &g, const uint8_t *d_codes, uint32_t *d_msa4, cudaStream_t st);
+int plm_build_buckets(const PlmGeom &g, const uint8_t *d_codes, uint16_t *d_perm, cudaStream_t st);
+int plm_expand(const PlmGeom &g, const float *d_x, float *d_W, cudaStream_t st);
+int plm_forward(const PlmGeom &g, const float *d_W, const float *d_x, const uint32_t *d_msa4,
+                const float *d_wts, float *d_R, float *d_gh_part, double *d_fx_part, cudaStream_t st);
+int plm_onehot_residual(const PlmGeom &g, const uint32_t *d_msa4, const float *d_wts, float *d_R,
+                        float *d_gh_part, cudaStream_t st);
+int plm_backward(const PlmGeom &g, const float *d_R, const uint16_t *d_perm, float *d_G, cudaStream_t st);
+int plm_finalize(const PlmGeom &g, const float *d_G, const float *d_gh_part, const double *d_fx_part,
+                 float *d_gh, float *d_gJ, double *d_fx, float scale_pair, cudaStream_t st);
+int plm_add_reg(const PlmGeom &g, const float *d_x, float *d_g, double *d_fx, float lambda_h,
+                float lambda_J, cudaStream_t st);
+
+// vecops.cu
+int vec_dot(const float *a, const float *b, int64_t n, double *out, cudaStream_t st);
+int vec_axpby(float *y, const float *x, float a, float b, int64_t n, cudaStream_t st);
+int vec_sub(float *out, const float *a, const float *b, int64_t n, cudaStream_t st);
+int lbfgs_direction(float *d, const float *g, const float *S, const float *Y, const double *ys,
+                    double *scratch, int64_t n, int m, int bound, int end, cudaStream_t st);
+int lbfgs_update_pair(float *s, float *y, const float *x, const float *xp, const float *g,
+                      const float *gp, double *ys, double *yy, int64_t n, cudaStream_t st);
+int fn_scores(const float *J, int L, int q, float *fn, cudaStream_t st);
+
+}  // namespace evc

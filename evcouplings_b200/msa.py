@@ -1,0 +1,167 @@
+"""
+Alignment ingest for the PLM engine: A2M/FASTA text -> uint8 code matrix.
+
+Mirrors what plmc does before inference (behaviour pinned
+by the golden run in the reference's notebooks/example/):
+
+* rows are upper-cased, '.' is a gap;
+* a row is invalid if ANY character of the row (insert columns included) is
+  outside alphabet + {'-', '.'} (case-insensitive);
+* focus mode: model sites = columns where the focus sequence has an upper-case
+  non-gap character; ``index_list`` numbers them by residue offset from the
+  ``/start-end`` of the focus header ("Region starts at");
+* with ignore_gaps (plmc -g) the gap (alphabet[0]) is not a model state: residues
+  are coded 0..q-1 in alphabet[1:] order and the gap is coded q.
+
+The reference side of this boundary is evcouplings/couplings/tools.py:213-233
+(focus name passed with ``/range`` stripped, alphabet with gap first).
+"""
+from collections import namedtuple
+
+import numpy as np
+
+ALPHABET_PROTEIN = "-ACDEFGHIKLMNPQRSTVWY"   # evcouplings/align/alignment.py:21-26
+
+EncodedAlignment = namedtuple("EncodedAlignment", [
+    "codes",            # (n_valid, L) uint8, C-contiguous
+    "valid",            # (n_total,) bool
+    "q",                # number of model states
+    "gap_code",         # -1 (gap is a state) or q (ignore_gaps)
+    "model_alphabet",   # str of length q
+    "focus_index",      # int or None
+    "focus_cols",       # (L,) int64 column indices into the raw alignment
+    "index_list",       # (L,) int32
+    "target_seq",       # str of length L
+    "region_start",     # int
+    "n_total", "n_valid", "num_total_sites",
+])
+
+
+class AlignmentError(ValueError):
+    pass
+
+
+def read_fasta_matrix(path):
+    """Read FASTA/A2M into (ids, uint8 matrix n_total x width of raw characters)."""
+    ids, chunks, cur = [], [], None
+    with open(path, "rb") as f:
+        for line in f:
+            if line.startswith(b">"):
+                if cur is not None:
+                    chunks.append(b"".join(cur))
+                ids.append(line[1:].strip().decode("ascii", "replace"))
+                cur = []
+            elif cur is not None:
+                cur.append(line.strip())
+    if cur is not None:
+        chunks.append(b"".join(cur))
+    if not chunks:
+        raise AlignmentError("alignment %s contains no sequences" % path)
+    width = len(chunks[0])
+    if width == 0:
+        raise AlignmentError("alignment %s has zero-length sequences" % path)
+    for k, c in enumerate(chunks):
+        if len(c) != width:
+            raise AlignmentError("ragged alignment: row %d has length %d, expected %d" % (k, len(c), width))
+    mat = np.frombuffer(b"".join(chunks), dtype=np.uint8).reshape(len(chunks), width)
+    return ids, mat
+
+
+def _find_focus(ids, focus):
+    key = focus.split("/")[0]
+    for k, name in enumerate(ids):
+        tok = name.split()[0] if name.split() else name
+        if tok == focus or tok.split("/")[0] == key:
+            return k, tok
+    raise AlignmentError("focus sequence %r not found in alignment" % focus)
+
+
+def encode_alignment(ids, raw, focus=None, alphabet=None, ignore_gaps=False):
+    """raw: (n_total, width) uint8 characters.  Returns EncodedAlignment."""
+    if alphabet is None:
+        alphabet = ALPHABET_PROTEIN
+    if len(set(alphabet)) != len(alphabet):
+        raise AlignmentError("alphabet has repeated characters")
+    gap = alphabet[0]
+    n_total, width = raw.shape
+
+    upper = np.arange(256, dtype=np.uint8)
+    upper[ord("a"):ord("z") + 1] -= 32
+    up = upper[raw]
+
+    focus_index, region_start = None, 1
+    if focus is not None:
+        focus_index, tok = _find_focus(ids, focus)
+        if "/" in tok:
+            try:
+                region_start = int(tok.split("/")[-1].split("-")[0])
+            except ValueError:
+                region_start = 1
+        frow = raw[focus_index]
+        is_gap = (frow == ord(gap)) | (frow == ord(".")) | (frow == ord("-"))
+        is_upper = (upper[frow] == frow)
+        residue_offset = np.cumsum(~is_gap) - 1
+        keep = (~is_gap) & is_upper
+        cols = np.nonzero(keep)[0]
+        index_list = (region_start + residue_offset[cols]).astype(np.int32)
+        num_total_sites = int((~is_gap).sum())
+    else:
+        cols = np.arange(width)
+        index_list = np.arange(1, width + 1, dtype=np.int32)
+        num_total_sites = width
+    if len(cols) < 2:
+        raise AlignmentError("fewer than 2 model sites selected")
+
+    allowed = np.zeros(256, dtype=bool)
+    for ch in alphabet:
+        allowed[ord(ch)] = True
+    allowed[ord("-")] = True
+    allowed[ord(".")] = True
+    valid = allowed[up].all(axis=1)
+
+    lut = np.full(256, 255, dtype=np.uint8)
+    if ignore_gaps:
+        q = len(alphabet) - 1
+        for k, ch in enumerate(alphabet[1:]):
+            lut[ord(ch)] = k
+        lut[ord(gap)] = q
+        lut[ord("-")] = q
+        lut[ord(".")] = q
+        gap_code = q
+        model_alphabet = alphabet[1:]
+    else:
+        q = len(alphabet)
+        for k, ch in enumerate(alphabet):
+            lut[ord(ch)] = k
+        lut[ord("-")] = 0
+        lut[ord(".")] = 0
+        gap_code = -1
+        model_alphabet = alphabet
+    codes = np.ascontiguousarray(lut[up[valid][:, cols]])
+    if focus_index is not None:
+        target = bytes(up[focus_index, cols]).decode("ascii")
+    else:
+        target = bytes(up[0, cols]).decode("ascii").replace(".", "-")
+    return EncodedAlignment(
+        codes=codes, valid=valid, q=q, gap_code=gap_code, model_alphabet=model_alphabet,
+        focus_index=focus_index, focus_cols=cols.astype(np.int64), index_list=index_list,
+        target_seq=target, region_start=region_start, n_total=n_total,
+        n_valid=int(valid.sum()), num_total_sites=num_total_sites,
+    )
+
+
+def load_alignment(path, focus=None, alphabet=None, ignore_gaps=False):
+    ids, raw = read_fasta_matrix(path)
+    return encode_alignment(ids, raw, focus=focus, alphabet=alphabet, ignore_gaps=ignore_gaps)
+
+
+def identity_threshold_count(theta, L):
+    """Integer form of the in-tree rule ``pair_id / L >= theta``
+    (evcouplings/align/alignment.py:1229): the smallest count c with
+    c / float(L) >= theta, evaluated in the same float64 arithmetic."""
+    c = int(theta * L)
+    while c > 0 and (c - 1) / float(L) >= theta:
+        c -= 1
+    while c / float(L) < theta:
+        c += 1
+    return c

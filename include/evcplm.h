@@ -1,0 +1,133 @@
+/*
+ * libevcplm -- C ABI of the B200-native pseudo-likelihood Potts-model engine.
+ *
+ * This is the drop-in boundary for the ONE numerically heavy step of the
+ * EVcouplings pipeline: what evcouplings/couplings/tools.py:126-307 (run_plmc)
+ * obtains today by fork/exec of the external `plmc` C/OpenMP binary
+ * (argv built at tools.py:202-262, subprocess at tools.py:266, caller
+ * evcouplings/couplings/protocol.py:203-218).  The entry points below are
+ * what a ctypes binding of that call site needs (INTEGRATION.md shows the
+ * binding); evcouplings_b200/ is the Python host that mirrors run_plmc on top
+ * of them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - "d_" arguments are device pointers on the handle's device, "h_"/unprefixed
+ *     host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - every function returns 0 on success, non-zero on failure;
+ *     evc_last_error() gives the message (thread-local).
+ *   - the caller owns all buffers it passes; the library owns what it allocates
+ *     inside a handle until evc_plm_destroy.
+ *   - a handle is not re-entrant; independent handles may be used from
+ *     different threads / processes (one process per GPU for multi-GPU runs).
+ *
+ * Parameter vector layout (identical to the plmc_v2 .model file read by
+ * evcouplings/couplings/model.py:354-389):
+ *     x = [ h : L*q floats | J : L(L-1)/2 blocks of q*q floats,
+ *           pairs (i<j) in row-major (i,j) order, block[a][b], a = state at i ]
+ * Sequence codes: uint8, 0..q-1 = model states; with gap_code >= 0 (plmc -g,
+ * "ignore_gaps") the value gap_code (== q) marks a gap: the site is skipped as
+ * a conditional and contributes nothing as a neighbour.
+ */
+#ifndef EVCPLM_H
+#define EVCPLM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVCPLM_ABI_VERSION 1
+
+typedef struct evc_plm evc_plm_t;
+
+/* ---- library / device -------------------------------------------------- */
+int evc_abi_version(void);
+const char *evc_last_error(void);
+int evc_device_count(void);                  /* <0 on error                */
+int evc_device_info(int32_t device, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
+                    int64_t *total_mem_bytes);
+
+/* ---- (b) O(N^2 L) pairwise-Hamming sequence reweighting ------------------
+ * Replaces plmc's reweighting pass (stderr "Effective number of samples",
+ * parsed at tools.py:55) and the in-tree twin
+ * evcouplings/align/alignment.py:1192-1233 (num_cluster_members).
+ * counts[s] = #{ t : #(codes[s,k] == codes[t,k]) >= min_identical }, self
+ * included, gap == gap counts as identical.  min_identical is the integer form
+ * of "pair_id / L >= theta" (alignment.py:1229), computed by the host.
+ */
+int evc_hamming_counts(const uint8_t *codes, int64_t N, int32_t L, int32_t min_identical,
+                       int32_t device, int32_t *counts_out);
+
+/* device-resident building blocks (multi-GPU: each rank counts a tile range,
+ * the host all-reduces the int32 counters) */
+int64_t evc_hamming_plane_words(int64_t N, int32_t L);   /* uint32 words of the bit-plane buffer */
+int64_t evc_hamming_num_tiles(int64_t N);                /* upper-triangular 128x128 pair tiles   */
+int evc_hamming_pack(const uint8_t *d_codes, int64_t N, int32_t L, uint32_t *d_planes, void *stream);
+int evc_hamming_count_tiles(const uint32_t *d_planes, int64_t N, int32_t L, int32_t min_identical,
+                            int64_t tile_begin, int64_t tile_end, int32_t *d_counts /* += */,
+                            void *stream);
+
+/* ---- (a) PLM objective + gradient -----------------------------------------
+ * Replaces plmc's negative-log-posterior evaluation (the inner loop of its
+ * L-BFGS).
+ */
+int evc_plm_create(evc_plm_t **out, const uint8_t *codes /* host, N x L */, int64_t N, int32_t L,
+                   int32_t q, int32_t gap_code /* -1: gap is a model state */,
+                   const float *weights /* host, N */, int32_t device);
+void evc_plm_destroy(evc_plm_t *h);
+int64_t evc_plm_num_params(const evc_plm_t *h);          /* L*q + L(L-1)/2*q*q */
+
+/* data term on this handle's sequences:  d_g[0..n) = d/dx of
+ * -sum_s w_s sum_i log P(s_i | s_-i),  d_fx[0] = that sum (double).
+ * No regulariser (so shards can be summed with one all-reduce). */
+int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, void *stream);
+
+/* Per-stage device timing of the LAST evc_plm_eval_data call (CUDA events recorded on the stream the
+ * kernels were launched on): ms_out[4] = {expand + clear, forward kernel, backward kernel, finalize}.
+ * Used by bench.py to report the dominant kernel's roofline live. */
+int evc_plm_set_profiling(evc_plm_t *h, int32_t enable);
+int evc_plm_last_stage_ms(evc_plm_t *h, float *ms_out);
+
+/* d_g += 2*lambda*x (lambda_h on the first L*q entries, lambda_J on the rest);
+ * d_fx[1] = d_fx[0] + lambda_h*|h|^2 + lambda_J*|J|^2   (d_fx[0] = -loglk kept) */
+int evc_plm_add_regulariser(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx,
+                            float lambda_h, float lambda_J, void *stream);
+
+/* host-buffer convenience (H2D of x, evaluation, D2H of g inside the call):
+ * fx_out[0] = -loglk, fx_out[1] = full objective. */
+int evc_plm_eval_host(evc_plm_t *h, const float *x, float *g, double *fx_out,
+                      float lambda_h, float lambda_J);
+
+/* ---- a6: weighted single / pair counts for the .model file ---------------
+ * d_fi_counts[L*q], d_fij_counts[L(L-1)/2*q*q] (tri blocks [a][b]) receive
+ * sum_s w_s [s_i=a] and sum_s w_s [s_i=a][s_j=b]; the host normalises
+ * (N_eff, or per-site / per-pair non-gap weight under ignore_gaps). */
+int evc_plm_weighted_counts(evc_plm_t *h, float *d_fi_counts, float *d_fij_counts, void *stream);
+
+/* ---- a8: on-device L-BFGS vector algebra ----------------------------------
+ * All scalars stay on the device (double); the host reads back only what the
+ * line search needs. */
+int evc_vec_dot(const float *d_a, const float *d_b, int64_t n, double *d_out, void *stream);
+int evc_vec_axpby(float *d_y, const float *d_x, float a, float b, int64_t n, void *stream); /* y = a*x + b*y */
+int evc_vec_copy(float *d_dst, const float *d_src, int64_t n, void *stream);
+int evc_vec_sub(float *d_out, const float *d_a, const float *d_b, int64_t n, void *stream);
+/* two-loop recursion: d = -H g using `bound` stored pairs ending before slot
+ * `end` (ring of m); d_S/d_Y are m x n row-major; d_ys[m] holds y.s per slot;
+ * d_scratch needs m + 2 doubles. */
+int evc_lbfgs_direction(float *d_d, const float *d_g, const float *d_S, const float *d_Y,
+                        const double *d_ys, double *d_scratch, int64_t n, int32_t m,
+                        int32_t bound, int32_t end, void *stream);
+/* s = x - xp, y = g - gp into slot, d_ys[slot] = y.s, d_scratch[0] = y.y (fused) */
+int evc_lbfgs_update_pair(float *d_S_slot, float *d_Y_slot, const float *d_x, const float *d_xp,
+                          const float *d_g, const float *d_gp, double *d_ys_slot, double *d_yy,
+                          int64_t n, void *stream);
+
+/* ---- a10: EC scores (Frobenius norm of each J block, raw gauge) ---------- */
+int evc_fn_scores(const float *d_J_tri, int32_t L, int32_t q, float *d_fn /* L(L-1)/2 */, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVCPLM_H */

@@ -1,0 +1,379 @@
+"""
+GPU parity tests (-m gpu): the CUDA path, called through the C ABI of libevcplm.so, against the CPU
+oracle (oracle/) on the same seeded inputs and against the committed golden fixtures.  Integer work
+(Hamming counts) must be bit-exact; floating point is fp32 on the device and is compared with the
+float64 oracle at the tolerances written in each test.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from evcouplings_b200 import _lib, lbfgs, model_io, msa, synthetic, tools  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+from oracle import plm_oracle as po  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    l = _lib.load()
+    _lib.require_device()
+    return l
+
+
+@pytest.fixture(scope="module")
+def engine(lib):
+    from evcouplings_b200.engine import CudaEngine
+    return CudaEngine()
+
+
+def gpu_hamming(lib, codes, thr):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    N, L = codes.shape
+    out = np.zeros(N, dtype=np.int32)
+    _lib.check(lib.evc_hamming_counts(codes.ctypes.data_as(ctypes.c_void_p), N, L, thr, 0,
+                                      out.ctypes.data_as(ctypes.c_void_p)), "evc_hamming_counts")
+    return out
+
+
+def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    N, L = codes.shape
+    h = ctypes.c_void_p()
+    _lib.check(lib.evc_plm_create(ctypes.byref(h), codes.ctypes.data_as(ctypes.c_void_p), N, L, q, gap_code,
+                                  w.ctypes.data_as(ctypes.c_void_p), 0), "evc_plm_create")
+    try:
+        assert lib.evc_plm_num_params(h) == x.size
+        g = np.zeros_like(x)
+        fx = np.zeros(2, dtype=np.float64)
+        _lib.check(lib.evc_plm_eval_host(h, x.ctypes.data_as(ctypes.c_void_p), g.ctypes.data_as(ctypes.c_void_p),
+                                         fx.ctypes.data_as(ctypes.c_void_p), lam_h, lam_J), "evc_plm_eval_host")
+    finally:
+        lib.evc_plm_destroy(h)
+    return fx[1], g, fx[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# (b) Hamming reweighting: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_hamming_golden_intree_twins(lib, golden_dir):
+    """against counts produced by the reference's own num_cluster_members (alignment.py:1192-1233)"""
+    d = np.load(os.path.join(golden_dir, "intree_twins.npz"))
+    for name in ("cfg1", "tie", "odd"):
+        codes = d[name + "_codes"]
+        thr = msa.identity_threshold_count(float(d[name + "_theta"]), codes.shape[1])
+        assert np.array_equal(gpu_hamming(lib, codes, thr), d[name + "_counts"])
+
+
+@pytest.mark.parametrize("N,L,theta,seed", [(1, 5, 0.8, 0), (2, 31, 0.5, 1), (127, 32, 0.8, 2), (129, 33, 0.8, 3),
+                                            (1000, 97, 0.7, 4), (3001, 200, 0.8, 5), (5000, 300, 0.8, 6),
+                                            (777, 800, 0.9, 7)])
+def test_hamming_vs_oracle(lib, N, L, theta, seed):
+    codes = synthetic.synthetic_msa_codes(N, L, seed)
+    thr = msa.identity_threshold_count(theta, L)
+    assert np.array_equal(gpu_hamming(lib, codes, thr), co.hamming_counts(codes, thr))
+
+
+def test_hamming_edge_thresholds(lib):
+    codes = synthetic.synthetic_msa_codes(300, 40, 11)
+    codes[17] = codes[3]                      # exact duplicates
+    assert (gpu_hamming(lib, codes, 0) == 300).all()            # everything is a neighbour
+    got = gpu_hamming(lib, codes, 40)                           # only exact duplicates
+    assert np.array_equal(got, co.hamming_counts(codes, 40)) and got[17] >= 2
+    assert (gpu_hamming(lib, codes, 41) == 0).all()             # unreachable threshold
+    all_gap = np.zeros((50, 64), dtype=np.uint8)
+    assert (gpu_hamming(lib, all_gap, 64) == 50).all()          # gap == gap is an identity
+    hi = np.full((40, 10), 31, dtype=np.uint8)                  # largest representable code
+    assert (gpu_hamming(lib, hi, 10) == 40).all()
+
+
+def test_hamming_pabp_golden_counts(lib, golden_dir):
+    """exact equality with the neighbour counts plmc itself stored (golden PABP run), full 151,496 x 82"""
+    c = np.load(os.path.join(golden_dir, "pabp_codes.npz"))
+    valid = np.unpackbits(c["valid_packed"])[: int(c["n_total"])].astype(bool)
+    gold = c["golden_counts_all"][valid]
+    got = gpu_hamming(lib, c["codes"], msa.identity_threshold_count(0.8, 82))
+    assert np.array_equal(got, gold)
+    assert abs((1.0 / got).sum() - 18615.48) < 0.01
+
+
+def test_hamming_full_size_sampled_rows(lib):
+    """BASELINE config 3 shape (N=200k, L=300): every sampled row equals the oracle's count."""
+    N, L = 200000, 300
+    codes = synthetic.synthetic_msa_codes(N, L, 3)
+    thr = msa.identity_threshold_count(0.8, L)
+    got = gpu_hamming(lib, codes, thr)
+    for r0 in (0, 99968, N - 48):
+        ref = co.hamming_counts(codes, thr, rows=(r0, r0 + 48))
+        assert np.array_equal(got[r0:r0 + 48], ref)
+    assert got.min() >= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# (a) PLM objective + gradient: fp32 device vs float64 oracle
+# ------------------------------------------------------------------------------------------------
+def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1):
+    rng = np.random.default_rng(seed)
+    codes = synthetic.synthetic_msa_codes(N, L, seed)
+    if gap:
+        codes = synthetic.to_ignore_gaps_codes(codes)
+    if q in (4, 5):
+        codes = (codes % 5).astype(np.uint8)
+        if gap:
+            codes = np.where(codes == 4, 4, codes).astype(np.uint8)   # 4 == gap code for q=4
+    w = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    n = L * q + L * (L - 1) // 2 * q * q
+    x = rng.normal(0, xscale, n).astype(np.float32)
+    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J)
+    fx64, g64, nll64 = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, lam_h, lam_J, "f64")
+    # tolerance: fp32 accumulation over N sequences; measured error of the CPU fp32 port is the yardstick
+    fx32, g32, _ = co.plm_eval(codes, w, x, q, lam_h, lam_J, "f32")
+    err_gpu = np.abs(g - g64).max()
+    err_c32 = np.abs(g32 - g64).max()
+    scale = np.abs(g64).max()
+    assert abs(fx - fx64) <= 2e-6 * abs(fx64), (fx, fx64)
+    assert abs(nll - nll64) <= 2e-6 * abs(nll64)
+    assert err_gpu <= max(3.0 * err_c32, 2e-6 * scale), (err_gpu, err_c32, scale)
+    assert np.linalg.norm(g - g64) <= 5e-6 * np.linalg.norm(g64)
+    return err_gpu, err_c32
+
+
+@pytest.mark.parametrize("N,L,q,gap,seed", [
+    (200, 40, 21, False, 1),        # BASELINE config 1 shape
+    (200, 40, 20, True, 1),         # ... with ignore_gaps (pipeline default)
+    (1, 2, 21, False, 2),           # smallest legal problem
+    (513, 33, 21, False, 3),        # ragged: N not a tile multiple, L not a multiple of 4
+    (2049, 26, 20, True, 4),        # crosses a backward tile (2048) by one sequence
+    (700, 97, 21, False, 5),
+    (3000, 64, 20, True, 6),
+    (300, 30, 5, False, 7),         # nucleotide alphabets
+    (300, 30, 4, True, 8),
+])
+def test_plm_eval_vs_oracle(lib, N, L, q, gap, seed):
+    _check_eval(lib, N, L, q, gap, seed)
+
+
+def test_plm_eval_zero_and_large_params(lib):
+    _check_eval(lib, 400, 24, 21, False, 9, xscale=0.0)          # x = 0: uniform softmax
+    _check_eval(lib, 400, 24, 21, False, 10, xscale=1.0)         # large couplings: peaked softmax
+
+
+def test_plm_eval_all_gap_column_ignore_gaps(lib):
+    """a column that is entirely gaps contributes nothing and receives no data gradient"""
+    codes = synthetic.to_ignore_gaps_codes(synthetic.synthetic_msa_codes(256, 12, 3))
+    codes[:, 5] = 20
+    w = np.ones(256, dtype=np.float32)
+    n = 12 * 20 + 66 * 400
+    x = np.random.default_rng(0).normal(0, 0.1, n).astype(np.float32)
+    fx, g, nll = gpu_eval_host(lib, codes, w, x, 20, 20, 0.0, 0.0)
+    fx64, g64, _ = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), 20, 0.0, 0.0, "f64")
+    assert np.abs(g - g64).max() < 1e-4
+    assert np.abs(g[5 * 20:6 * 20]).max() == 0.0
+
+
+def test_plm_create_rejects_bad_arguments(lib):
+    codes = np.zeros((4, 6), dtype=np.uint8)
+    w = np.ones(4, dtype=np.float32)
+    h = ctypes.c_void_p()
+    for q, gap in ((7, -1), (21, 5)):
+        rc = lib.evc_plm_create(ctypes.byref(h), codes.ctypes.data_as(ctypes.c_void_p), 4, 6, q, gap,
+                                w.ctypes.data_as(ctypes.c_void_p), 0)
+        assert rc != 0 and lib.evc_last_error()
+    rc = lib.evc_plm_create(ctypes.byref(h), codes.ctypes.data_as(ctypes.c_void_p), 0, 6, 21, -1,
+                            w.ctypes.data_as(ctypes.c_void_p), 0)
+    assert rc != 0
+
+
+def test_weighted_counts_vs_oracle(engine):
+    for gap in (False, True):
+        codes = synthetic.synthetic_msa_codes(900, 30, 21)
+        if gap:
+            codes = synthetic.to_ignore_gaps_codes(codes)
+        q = 20 if gap else 21
+        w = (1.0 / co.hamming_counts(codes, 24)).astype(np.float32)
+        prob = engine.plm_problem(codes, w, q, q if gap else -1, 0.01, 1.0)
+        fic, fijc = prob.weighted_counts()
+        prob.close()
+        fi, fij = model_io.normalise_frequencies(fic, fijc, float(w.sum()), gap)
+        fi_o, fij_o = po.frequencies(codes, w.astype(np.float64), q, q if gap else -1)
+        assert np.abs(fi - fi_o).max() < 2e-6 and np.abs(fij - fij_o).max() < 2e-6
+
+
+def test_pabp_frequencies_golden(engine, golden_dir):
+    """f_i / f_ij from the CUDA path vs the values plmc wrote into the golden .model (<= 1e-6 + fp32 noise)"""
+    c = np.load(os.path.join(golden_dir, "pabp_codes.npz"))
+    g = np.load(os.path.join(golden_dir, "pabp_golden.npz"))
+    valid = np.unpackbits(c["valid_packed"])[: int(c["n_total"])].astype(bool)
+    w = (1.0 / c["golden_counts_all"][valid]).astype(np.float32)
+    prob = engine.plm_problem(c["codes"], w, 20, 20, 0.01, 16.2)
+    fic, fijc = prob.weighted_counts()
+    prob.close()
+    fi, fij = model_io.normalise_frequencies(fic, fijc, float(w.sum()), True)
+    assert np.abs(fi - g["fi"]).max() < 5e-6
+    assert np.abs(fij[g["fij_pair_index"]] - g["fij_blocks"]).max() < 5e-6
+
+
+def test_pabp_gradient_balance_at_golden_optimum(engine, golden_dir):
+    """SURVEY row a7 pin, on the device: at plmc's own (h, J) the data gradient balances 2*lambda_J*J."""
+    c = np.load(os.path.join(golden_dir, "pabp_codes.npz"))
+    g = np.load(os.path.join(golden_dir, "pabp_golden.npz"))
+    valid = np.unpackbits(c["valid_packed"])[: int(c["n_total"])].astype(bool)
+    w = (1.0 / c["golden_counts_all"][valid]).astype(np.float32)
+    prob = engine.plm_problem(c["codes"], w, 20, 20, 0.0, 0.0)
+    x = np.concatenate([g["h"].ravel(), g["J"].ravel()]).astype(np.float32)
+    prob.set_x(x)
+    prob.evaluate(prob.x)
+    grad = prob.g.cpu().numpy()
+    prob.close()
+    gJ = grad[82 * 20:].reshape(-1, 20, 20)
+    for k in g["fij_pair_index"]:
+        J = g["J"][k].astype(np.float64)
+        m = np.abs(J) > 0.02
+        assert 0.9 < np.median(-gJ[k][m] / (2 * 16.2 * J[m])) < 1.1
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: device L-BFGS algebra vs numpy
+# ------------------------------------------------------------------------------------------------
+def test_lbfgs_vector_algebra(engine):
+    import torch
+    codes = synthetic.synthetic_msa_codes(64, 9, 2)
+    prob = engine.plm_problem(codes, np.ones(64, dtype=np.float32), 21, -1, 0.01, 1.0, m=4)
+    n, m = prob.n, 4
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    assert abs(prob.dot(ta, tb) - float(np.dot(a.astype(np.float64), b.astype(np.float64)))) < 1e-9 * n
+    prob.axpby(ta, tb, 0.5, 2.0)
+    assert np.allclose(ta.cpu().numpy(), 0.5 * b + 2.0 * a, rtol=1e-6, atol=1e-6)
+    # build a history of 6 updates in a ring of 4 and compare the direction with a numpy two-loop
+    from cpu_engine import OracleProblem
+    ref = OracleProblem(codes, np.ones(64), 21, -1, 0.01, 1.0, m=m)
+    end = 0
+    for k in range(1, 7):
+        xp, gp = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+        s = (0.1 * rng.normal(size=n)).astype(np.float32)
+        xn = xp + s
+        gn = (gp + s * rng.uniform(0.5, 2.0, n).astype(np.float32)).astype(np.float32)   # y.s > 0
+        prob.x.copy_(torch.from_numpy(xn)); prob.g.copy_(torch.from_numpy(gn))
+        prob.xp.copy_(torch.from_numpy(xp)); prob.gp.copy_(torch.from_numpy(gp))
+        prob.update_pair(end, prob.xp, prob.gp)
+        ref.x[:], ref.g[:] = xn, gn
+        ref.update_pair(end, (xn - s.astype(np.float64)) * 0 + xp, gp.astype(np.float64))
+        end = (end + 1) % m
+        bound = min(m, k)
+        prob.direction(prob.d, bound, end)
+        ref.direction(ref.d, bound, end)
+        got = prob.d.cpu().numpy()
+        assert np.linalg.norm(got - ref.d) <= 2e-5 * np.linalg.norm(ref.d), k
+    prob.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end through run_plmc (the reference-facing plugin)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ignore_gaps", [False, True])
+def test_run_plmc_config1_vs_oracle_optimum(engine, tmp_path, ignore_gaps):
+    """BASELINE config 1 (N=200, L=40): fitted h, J and EC scores vs the float64 oracle optimum.
+    Tolerances (north star): CN rms <= 1e-4; parameters max abs <= 2e-3."""
+    N, L = 200, 40
+    codes = synthetic.synthetic_msa_codes(N, L, 1)
+    a2m = tmp_path / "cfg1.a2m"
+    synthetic.write_a2m(str(a2m), codes)
+    q = 20 if ignore_gaps else 21
+    lam_J = 0.01 * (q - 1) * (L - 1)
+    res, run = tools.run_plmc(str(a2m), str(tmp_path / "o_ECs.txt"), str(tmp_path / "o.model"), focus_seq="seq0/1-40",
+                              theta=0.8, ignore_gaps=ignore_gaps, iterations=3000, lambda_h=0.01, lambda_J=lam_J,
+                              engine=engine, return_run=True, epsilon=1e-5)
+    ali = run.alignment
+    counts_o = co.hamming_counts(ali.codes, msa.identity_threshold_count(0.8, L))
+    assert np.array_equal(run.counts, counts_o)
+    w = 1.0 / counts_o
+    xo, info = po.fit(ali.codes, w, q, 0.01, lam_J, ali.gap_code, x0=tools.initial_point(
+        po.frequencies(ali.codes, w, q, ali.gap_code)[0], w.sum(), L, q).astype(np.float64), max_iter=4000)
+    m = po.read_model(str(tmp_path / "o.model"))
+    x = np.concatenate([m["h"].ravel(), m["J"].ravel()]).astype(np.float64)
+    cn = np.loadtxt(str(tmp_path / "o_ECs.txt"), usecols=5)
+    cn_o = po.cn_scores(xo[L * q:].reshape(-1, q, q), L)
+    print("status", res.optimization_status, "iters", run.lbfgs.iterations, "evals", run.lbfgs.evaluations,
+          "max|dx|", np.abs(x - xo).max(), "cn rms", np.sqrt(np.mean((cn - cn_o) ** 2)))
+    assert np.sqrt(np.mean((cn - cn_o) ** 2)) <= 1e-4
+    assert np.abs(x - xo).max() <= 2e-3
+    assert res.num_valid_seqs == N and res.num_valid_sites == L
+    fi_o, fij_o = po.frequencies(ali.codes, w, q, ali.gap_code)
+    assert np.abs(m["fi"] - fi_o).max() < 2e-6 and np.abs(m["fij"] - fij_o).max() < 2e-6
+
+
+def test_run_plmc_iteration_capped_trajectory_matches_host_logic(engine, tmp_path):
+    """same L-BFGS control logic, device vs oracle backend, 15 iterations from the same start:
+    trajectories agree to fp32 noise (fx within 1e-5 relative at every iteration)."""
+    from cpu_engine import OracleEngine
+    codes = synthetic.synthetic_msa_codes(300, 24, 4)
+    a2m = tmp_path / "t.a2m"
+    synthetic.write_a2m(str(a2m), codes)
+    kw = dict(focus_seq="seq0", theta=0.8, iterations=15, lambda_h=0.01, lambda_J=0.01 * 20 * 23, return_run=True)
+    r1, run1 = tools.run_plmc(str(a2m), str(tmp_path / "g_ECs.txt"), str(tmp_path / "g.model"), engine=engine, **kw)
+    r2, run2 = tools.run_plmc(str(a2m), str(tmp_path / "c_ECs.txt"), str(tmp_path / "c.model"),
+                              engine=OracleEngine(), **kw)
+    f1 = r1.iteration_table["fx"].astype(float).values
+    f2 = r2.iteration_table["fx"].astype(float).values
+    assert len(f1) == len(f2) == 15
+    assert np.abs(f1 - f2).max() <= 1e-5 * np.abs(f2).max()
+    assert np.abs(run1.x - run2.x).max() < 5e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# full BASELINE size (config 2: N=50k, L=200, q=21): size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties(engine):
+    import torch
+    N, L, q = 50000, 200, 21
+    codes = synthetic.synthetic_msa_codes(N, L, 2)
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    n = L * q + L * (L - 1) // 2 * q * q
+    x = rng.normal(0, 0.05, n).astype(np.float32)
+    full = engine.plm_problem(codes, w, q, -1, 0.0, 0.0)
+    full.set_x(x)
+    f_full = full.evaluate(full.x)
+    g_full = full.g.clone()
+    # (1) shards add up: data term is a sum over sequences
+    half = N // 2 + 77
+    pa = engine.plm_problem(codes[:half], w[:half], q, -1, 0.0, 0.0)
+    pb = engine.plm_problem(codes[half:], w[half:], q, -1, 0.0, 0.0)
+    pa.set_x(x); pb.set_x(x)
+    fa, fb = pa.evaluate(pa.x), pb.evaluate(pb.x)
+    assert abs((fa + fb) - f_full) <= 1e-9 * abs(f_full) + 1e-3
+    gsum = pa.g + pb.g
+    assert float((gsum - g_full).norm() / g_full.norm()) < 2e-6
+    pa.close(); pb.close()
+    # (2) linear in the weights
+    p2 = engine.plm_problem(codes, 2.0 * w, q, -1, 0.0, 0.0)
+    p2.set_x(x)
+    f2 = p2.evaluate(p2.x)
+    assert abs(f2 - 2 * f_full) <= 1e-7 * abs(f_full)
+    assert float((p2.g - 2 * g_full).norm() / g_full.norm()) < 2e-6
+    p2.close()
+    # (3) gradient is the derivative of fx along a random direction (central difference)
+    d = torch.from_numpy(rng.normal(0, 1.0, n).astype(np.float32)).cuda()
+    d /= d.norm()
+    eps = 2e-2
+    xs = torch.from_numpy(x).cuda()
+    fp = full.evaluate(xs + eps * d)
+    fm = full.evaluate(xs - eps * d)
+    dd = float((g_full.double() * d.double()).sum())
+    assert abs((fp - fm) / (2 * eps) - dd) <= 2e-3 * abs(dd) + 1e-2
+    # (4) sampled sequences subset against the oracle at full L (N_sub = 1500)
+    full.close()
+    sub = engine.plm_problem(codes[:1500], w[:1500], q, -1, 0.0, 0.0)
+    sub.set_x(x)
+    fs = sub.evaluate(sub.x)
+    fo, go, _ = co.plm_eval(codes[:1500], w[:1500].astype(np.float64), x.astype(np.float64), q, 0.0, 0.0, "f64")
+    assert abs(fs - fo) <= 2e-6 * abs(fo)
+    assert np.linalg.norm(sub.g.cpu().numpy() - go) <= 5e-6 * np.linalg.norm(go)
+    sub.close()
