@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the PLM hot path (BASELINE.json metric).
+
+Metric: PLM gradient evaluations expressed as cell-ops/s, one cell-op = one (n, i, j, a) term,
+N * L^2 * q per objective+gradient evaluation.  Workload at 1 GPU = BASELINE
+configs[1]: synthetic MSA N=50,000, L=200, q=21 (gap is a state), fp32.  A "step" is one evaluation
+of the objective and its full gradient (expand -> forward -> backward -> symmetrise -> all-reduce ->
+regulariser) for a fixed parameter vector.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
+
+N > 1: launched by torchrun, one rank per GPU; sequences sharded over ranks, ONE NCCL all-reduce of the
+gradient per step (+ an 8-byte one for -loglk).  Default `weak`: 50,000 sequences per GPU (the 8-GPU
+point is the Pfam-scale sharded case, BASELINE configs[3] territory); `--scaling strong` keeps
+N=50,000 total.
+
+`--impl reference`: the reference's plmc C/OpenMP binary is not available (source not vendored, no
+network), so the CPU arm times oracle/plm_oracle_c.c -- a site-parallel C/OpenMP fp32 port of the
+same objective (kind "port") -- on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU, L, Q = 50000, 200, 21
+LAMBDA_H, LAMBDA_J = 0.01, 0.01 * (Q - 1) * (L - 1)
+SEED = 2
+METRIC = "PLM gradient evals/s as N*L^2*q cell-ops/s"
+UNIT = "cell-ops/s"
+CPU_SAMPLE_N = 5000
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        pw = max(float(s[2]) for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "power_w_max": pw,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(n_total):
+    from evcouplings_b200 import synthetic
+    codes = synthetic.synthetic_msa_codes(n_total, L, SEED)
+    n = L * Q + L * (L - 1) // 2 * Q * Q
+    x = np.random.default_rng(SEED).normal(0.0, 0.05, n).astype(np.float32)
+    return codes, x
+
+
+def cpu_arm(codes, x, weights, steps, warmup, sample_n):
+    """Times the C/OpenMP fp32 port on `sample_n` sequences of the workload, all host threads."""
+    from oracle import c_oracle as co
+    co.build()
+    threads = co.max_threads()
+    c = np.ascontiguousarray(codes[:sample_n])
+    w = np.ascontiguousarray(weights[:sample_n], dtype=np.float32)
+    for _ in range(warmup):
+        co.plm_eval(c, w, x, Q, LAMBDA_H, LAMBDA_J, "f32")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.plm_eval(c, w, x, Q, LAMBDA_H, LAMBDA_J, "f32")
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    cells = float(sample_n) * L * L * Q
+    return cells / dt, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    codes, x = make_inputs(CPU_SAMPLE_N)
+    weights = np.random.default_rng(SEED + 1).uniform(0.05, 1.0, CPU_SAMPLE_N).astype(np.float32)
+    steps = max(1, args.steps)
+    value, dt, threads = cpu_arm(codes, x, weights, steps, min(args.warmup, 1), CPU_SAMPLE_N)
+    sample = "%d of the %d sequences (same generator/seed), L=%d q=%d, one full fx+gradient per step" % (
+        CPU_SAMPLE_N, N_PER_GPU, L, Q)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PLM fx+gradient, synthetic MSA N=%d L=%d q=%d fp32 (BASELINE configs[1])"
+                   % (N_PER_GPU, L, Q), "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "plmc itself is not vendored/buildable; C/OpenMP fp32 restatement (oracle/plm_oracle_c.c)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    from evcouplings_b200 import msa
+    from evcouplings_b200.engine import CudaEngine
+
+    engine = CudaEngine()
+    n_total = N_PER_GPU * world if args.scaling == "weak" else N_PER_GPU
+    codes, x = make_inputs(n_total)
+    n = x.size
+
+    # sequence weights from the real reweighting pass (hot path (b)), untimed setup
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    counts = engine.hamming_counts(codes, msa.identity_threshold_count(0.8, L))
+    torch.cuda.synchronize()
+    t_ham = time.perf_counter() - t0
+    weights = (1.0 / counts).astype(np.float32)
+
+    prob = engine.plm_problem(codes, weights, Q, -1, LAMBDA_H, LAMBDA_J)
+    prob.set_x(x)
+    engine.lib.evc_plm_set_profiling(prob.handle, 1)
+    cells = float(n_total) * L * L * Q
+    n_local = prob.shard[1] - prob.shard[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------
+    import ctypes
+    for _ in range(args.warmup):
+        prob.evaluate_async(prob.x)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = engine.kernel_launches
+    stage = np.zeros(4, dtype=np.float32)
+    stage_sum = np.zeros(4, dtype=np.float64)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        prob.evaluate_async(prob.x)
+        engine.lib.evc_plm_last_stage_ms(prob.handle, stage.ctypes.data_as(ctypes.c_void_p))
+        stage_sum += stage
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = engine.kernel_launches - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=engine.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    clocks = sampler.summary()
+    value = cells / (ms_step * 1e-3)
+    stage_ms = stage_sum / args.steps
+    fx_check = prob.fxbuf.tolist()
+
+    # ---- end to end through the public host API (host buffers, H2D + D2H inside) --------------
+    x_pin = torch.from_numpy(x).pin_memory()
+    g_pin = torch.empty(n, dtype=torch.float32).pin_memory()
+    for _ in range(min(args.warmup, 3)):
+        prob.evaluate_host(x_pin, g_pin)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fx_e2e = prob.evaluate_host(x_pin, g_pin)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=engine.device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = cells / float(te.item())
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    # Algorithmic bytes: 8 B per cell-op per evaluation = 4 B gathered coupling read in the
+    # forward kernel + 4 B gradient element reduced in the backward kernel, + N*L bytes of MSA.
+    peak, peak_src = measured_peak_hbm()
+    local_cells = float(n_local) * L * L * Q
+    names = ["expand+clear", "plm_fwd_kernel", "plm_bwd_kernel", "finalize"]
+    dom = 1 if stage_ms[1] >= stage_ms[2] else 2
+    alg_bytes = 4.0 * local_cells + float(n_local) * L
+    achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
+                "whole_eval": {"algorithmic_bytes": 2 * 4.0 * local_cells + n_local * L,
+                               "achieved": (8.0 * local_cells + n_local * L) / (ms_step * 1e-3) / 1e9,
+                               "frac": (8.0 * local_cells + n_local * L) / (ms_step * 1e-3) / 1e9 / peak},
+                "note": "on-chip-bound kernel: achieved > peak means the gathered bytes are served from shared "
+                        "memory/L2, not HBM (see DESIGN.md, profiles/)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PLM fx+gradient, synthetic MSA N=%d%s L=%d q=%d fp32 (BASELINE configs[1])"
+                   % (N_PER_GPU, " per GPU (sharded, N_total=%d)" % n_total if world > 1 else "", L, Q),
+                   "global_sequences": n_total, "parallelism": "dp%d (sequence shards, 1 NCCL all-reduce of %d floats/step)"
+                   % (world, n) if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (residual buffer %.0f MB, coupling tensors 2x%.0f MB per step)"
+                   % (n_local * L * 21 * 4 / 1e6, L * L * 441 * 4 / 1e6),
+                   "lambda_h": LAMBDA_H, "lambda_J": LAMBDA_J, "n_params": n},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": float(te.item()) * 1e3,
+                "h2d_bytes_per_step": int(4 * n), "d2h_bytes_per_step": int(4 * n + 16)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "fx": {"negloglk": fx_check[0], "objective": fx_check[1], "e2e_objective": fx_e2e},
+        "hamming_setup": {"pairs_per_s": 0.5 * n_total * (n_total - 1) / t_ham, "seconds": t_ham, "N": n_total,
+                          "note": "includes H2D + packing; untimed setup, not the benchmarked step"},
+    }
+    if rank == 0 and world == 1:
+        cb_value, cb_dt, threads = cpu_arm(codes, x, weights, 2, 1, CPU_SAMPLE_N)
+        line["cpu_baseline"] = {"value": cb_value, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d of the %d sequences, 2 timed evaluations after 1 warm-up (%.2f s each)"
+                                % (CPU_SAMPLE_N, n_total, cb_dt)}
+    if rank == 0:
+        print(json.dumps(line))
+    prob.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,16 @@ class CudaPlmProblem(object):
         self.last_negloglk = nll
         return fx
 
+    def evaluate_host(self, x_host, g_host):
+        """Public host-buffer entry: x_host / g_host are CPU float32 torch tensors (pinned for speed).
+        H2D of x, evaluation (incl. the all-reduce), D2H of the gradient and of fx, then synchronise."""
+        self.x.copy_(x_host, non_blocking=True)
+        self.evaluate_async(self.x)
+        g_host.copy_(self.g, non_blocking=True)
+        nll, fx = self.fxbuf.tolist()          # D2H of the result scalars; synchronises the stream
+        self.last_negloglk = nll
+        return fx
+
     # -- vector space protocol ------------------------------------------------------------------
     def dot(self, a, b):
         e = self.engine

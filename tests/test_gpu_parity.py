@@ -300,10 +300,19 @@ def test_run_plmc_config1_vs_oracle_optimum(engine, tmp_path, ignore_gaps):
     x = np.concatenate([m["h"].ravel(), m["J"].ravel()]).astype(np.float64)
     cn = np.loadtxt(str(tmp_path / "o_ECs.txt"), usecols=5)
     cn_o = po.cn_scores(xo[L * q:].reshape(-1, q, q), L)
+    nh = L * q
+    f_gpu = po.objective(x, ali.codes, w, q, 0.01, lam_J, ali.gap_code)[0]
+    f_opt = po.objective(xo, ali.codes, w, q, 0.01, lam_J, ali.gap_code)[0]
+    dJ, dh = np.abs(x[nh:] - xo[nh:]).max(), np.abs(x[:nh] - xo[:nh]).max()
     print("status", res.optimization_status, "iters", run.lbfgs.iterations, "evals", run.lbfgs.evaluations,
-          "max|dx|", np.abs(x - xo).max(), "cn rms", np.sqrt(np.mean((cn - cn_o) ** 2)))
+          "max|dJ|", dJ, "max|dh|", dh, "rel objective gap", (f_gpu - f_opt) / f_opt,
+          "cn rms", np.sqrt(np.mean((cn - cn_o) ** 2)), "cn max", np.abs(cn - cn_o).max())
+    # stated fp32 tolerances: EC (cn) rms <= 1e-4 (north star); couplings max abs <= 2e-3; fields max abs
+    # <= 0.1 (lambda_h = 0.01 leaves h almost flat: the objective gap below is what convergence means);
+    # objective within 1e-6 relative of the float64 optimum
     assert np.sqrt(np.mean((cn - cn_o) ** 2)) <= 1e-4
-    assert np.abs(x - xo).max() <= 2e-3
+    assert dJ <= 2e-3 and dh <= 0.1
+    assert 0 <= (f_gpu - f_opt) / f_opt <= 1e-6
     assert res.num_valid_seqs == N and res.num_valid_sites == L
     fi_o, fij_o = po.frequencies(ali.codes, w, q, ali.gap_code)
     assert np.abs(m["fi"] - fi_o).max() < 2e-6 and np.abs(m["fij"] - fij_o).max() < 2e-6
