@@ -21,7 +21,8 @@ struct evc_plm {
     PlmGeom g{};
     uint8_t *d_codes = nullptr;     // [N][L] (kept for bucket building only; freed after create)
     uint32_t *d_msa4 = nullptr;
-    uint16_t *d_perm = nullptr;
+    uint32_t *d_perm = nullptr;
+    uint16_t *d_bstart = nullptr;
     float *d_wts = nullptr;
     float *d_W = nullptr;
     float *d_G = nullptr;
@@ -130,6 +131,7 @@ void evc_plm_destroy(evc_plm_t *h)
     cudaFree(h->d_codes);
     cudaFree(h->d_msa4);
     cudaFree(h->d_perm);
+    cudaFree(h->d_bstart);
     cudaFree(h->d_wts);
     cudaFree(h->d_W);
     cudaFree(h->d_G);
@@ -182,7 +184,8 @@ int evc_plm_create(evc_plm_t **out, const uint8_t *codes, int64_t N, int32_t L, 
     const size_t w_bytes = (size_t)g.w_floats() * sizeof(float);
     bool ok = cudaMalloc(&h->d_codes, (size_t)N * L) == cudaSuccess &&
               cudaMalloc(&h->d_msa4, (size_t)g.L4 * g.Nld * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMalloc(&h->d_perm, (size_t)g.ntiles_b * L * PLM_BWD_TS * sizeof(uint16_t)) == cudaSuccess &&
+              cudaMalloc(&h->d_perm, (size_t)g.ntiles_b * L * PLM_BWD_CAP * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&h->d_bstart, (size_t)g.ntiles_b * L * PLM_BWD_BS * sizeof(uint16_t)) == cudaSuccess &&
               cudaMalloc(&h->d_wts, (size_t)N * sizeof(float)) == cudaSuccess &&
               cudaMalloc(&h->d_W, w_bytes) == cudaSuccess && cudaMalloc(&h->d_G, w_bytes) == cudaSuccess &&
               cudaMalloc(&h->d_R, (size_t)L * g.Nr * g.S * sizeof(float)) == cudaSuccess &&
@@ -198,7 +201,7 @@ int evc_plm_create(evc_plm_t **out, const uint8_t *codes, int64_t N, int32_t L, 
          cudaMemcpy(h->d_wts, weights, (size_t)N * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemset(h->d_W, 0, w_bytes) == cudaSuccess &&
          cudaMemset(h->d_R, 0, (size_t)L * g.Nr * g.S * sizeof(float)) == cudaSuccess;
-    if (!ok || plm_pack_msa(g, h->d_codes, h->d_msa4, 0) || plm_build_buckets(g, h->d_codes, h->d_perm, 0) ||
+    if (!ok || plm_pack_msa(g, h->d_codes, h->d_msa4, 0) || plm_build_buckets(g, h->d_codes, h->d_perm, h->d_bstart, 0) ||
         cudaDeviceSynchronize() != cudaSuccess) {
         if (ok) set_error(std::string("evc_plm_create: packing failed: ") + cudaGetErrorString(cudaGetLastError()));
         else set_error("evc_plm_create: H2D failed");
@@ -225,7 +228,7 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
     if (plm_forward(g, h->d_W, d_x, h->d_msa4, h->d_wts, h->d_R, h->d_gh_part, h->d_fx_part, st)) return 1;
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[2], st));
-    if (plm_backward(g, h->d_R, h->d_perm, h->d_G, st)) return 1;
+    if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
     if (plm_finalize(g, h->d_G, h->d_gh_part, h->d_fx_part, d_g, d_g + (int64_t)g.L * g.q, d_fx, 1.0f, st))
         return 1;
@@ -290,7 +293,7 @@ int evc_plm_weighted_counts(evc_plm_t *h, float *d_fi_counts, float *d_fij_count
     const PlmGeom &g = h->g;
     EVC_CUDA(cudaMemsetAsync(h->d_G, 0, (size_t)g.w_floats() * sizeof(float), st));
     if (plm_onehot_residual(g, h->d_msa4, h->d_wts, h->d_R, h->d_gh_part, st)) return 1;
-    if (plm_backward(g, h->d_R, h->d_perm, h->d_G, st)) return 1;
+    if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
     return plm_finalize(g, h->d_G, h->d_gh_part, nullptr, d_fi_counts, d_fij_counts, nullptr, 0.5f, st);
 }
 

@@ -34,16 +34,20 @@ struct PlmGeom {
 
 constexpr int PLM_FWD_TS = 512;    // sequences per forward CTA (256 threads x 2)
 constexpr int PLM_BWD_TS = 2048;   // sequences per backward tile (residual tile in shared memory)
+constexpr int PLM_BWD_CAP = 2224;  // list entries per (tile, column): 2048 + up to 7 pads for each of <= 22 buckets
+constexpr int PLM_BWD_BS = 24;     // bucket-boundary slots per list
 
 bool plm_supported_q(int q);
 int plm_pack_msa(const PlmGeom &g, const uint8_t *d_codes, uint32_t *d_msa4, cudaStream_t st);
-int plm_build_buckets(const PlmGeom &g, const uint8_t *d_codes, uint16_t *d_perm, cudaStream_t st);
+int plm_build_buckets(const PlmGeom &g, const uint8_t *d_codes, uint32_t *d_perm, uint16_t *d_bstart,
+                      cudaStream_t st);
 int plm_expand(const PlmGeom &g, const float *d_x, float *d_W, cudaStream_t st);
 int plm_forward(const PlmGeom &g, const float *d_W, const float *d_x, const uint32_t *d_msa4,
                 const float *d_wts, float *d_R, float *d_gh_part, double *d_fx_part, cudaStream_t st);
 int plm_onehot_residual(const PlmGeom &g, const uint32_t *d_msa4, const float *d_wts, float *d_R,
                         float *d_gh_part, cudaStream_t st);
-int plm_backward(const PlmGeom &g, const float *d_R, const uint16_t *d_perm, float *d_G, cudaStream_t st);
+int plm_backward(const PlmGeom &g, const float *d_R, const uint32_t *d_perm, const uint16_t *d_bstart,
+                 float *d_G, cudaStream_t st);
 int plm_finalize(const PlmGeom &g, const float *d_G, const float *d_gh_part, const double *d_fx_part,
                  float *d_gh, float *d_gJ, double *d_fx, float scale_pair, cudaStream_t st);
 int plm_add_reg(const PlmGeom &g, const float *d_x, float *d_g, double *d_fx, float lambda_h,

@@ -17,8 +17,9 @@
 //          sequence index fastest (a warp reads 128 contiguous bytes)
 //   R      [L][Nr][S]       residuals r for conditional i (written by forward,
 //          bulk-copied as one contiguous tile by backward)
-//   perm   [ntiles_b][L][2048] uint16 = (state << 11 | local sequence), the sequences
-//          of a 2048-sequence tile sorted by their state at column j (static per MSA)
+//   perm   [ntiles_b][L][2224] uint32 byte offsets of the tile's residual rows, grouped by the
+//          sequence's state at column j, buckets 8-aligned and padded with a zero row;
+//          bstart [ntiles_b][L][24] uint16 bucket boundaries (static per MSA)
 //   G      same geometry as W: G[i][j][b][a] = sum_n r_ni(a) [s_nj = b]
 //
 // Kernels
@@ -29,9 +30,9 @@
 //                  per sequence in registers; softmax in registers; writes R, per-CTA
 //                  partials of g_h and fx (deterministic two-stage reduction)
 //   plm_bwd        CTA = (2048-sequence tile, site i): R tile (172 KB) bulk-copied to shared
-//                  memory; warp = column j, lane = state a; walks the state-sorted
-//                  sequence list so that every (j, b) bucket is a register accumulation
-//                  of contiguous shared-memory rows, flushed with one RED per bucket
+//                  memory; warp = column j, lane = state a; every (j, b) bucket is a
+//                  branch-free register accumulation of shared-memory rows
+//                  (LDG.128 of 4 offsets -> 4 x (IADD, LDS, FADD)), one RED per bucket
 //   plm_finalize   g_J(i<j)[a][b] = G[i][j][b][a] + G[j][i][a][b]; g_h, fx from partials
 //   plm_add_reg    g += 2 lambda x, fx += lambda |x|^2 (deterministic reduction)
 //
@@ -78,37 +79,56 @@ int plm_pack_msa(const PlmGeom &g, const uint8_t *d_codes, uint32_t *d_msa4, cud
     return 0;
 }
 
-// state-sorted sequence lists per (backward tile, column): stable counting sort by one warp
-__global__ void build_buckets_kernel(const uint8_t *__restrict__ codes, uint16_t *__restrict__ perm,
-                                     int64_t N, int L, int q)
+// state-sorted sequence lists per (backward tile, column): stable counting sort by one warp.
+// Output per (tile, column): PLM_BWD_CAP uint32 byte offsets (row * S * 4) into the shared-memory residual
+// tile, grouped by state; every bucket starts at a multiple of 8 entries and is padded with the offset of
+// an all-zero row, so the consumer loop is branch-free.  bstart[b] .. bstart[b+1] (uint16, PLM_BWD_BS per
+// list) delimit bucket b; ignored-gap sequences are not listed at all.
+__global__ void build_buckets_kernel(const uint8_t *__restrict__ codes, uint32_t *__restrict__ perm,
+                                     uint16_t *__restrict__ bstart, int64_t N, int L, int q, int S)
 {
     __shared__ int hist[32];
+    __shared__ int start[33];
     const int t = blockIdx.x, j = blockIdx.y, lane = threadIdx.x;
     const int64_t base = (int64_t)t * PLM_BWD_TS;
     const int cnt = (int)min((int64_t)PLM_BWD_TS, N - base);
     const int cnt32 = (cnt + 31) & ~31;
-    uint16_t *out = perm + ((int64_t)t * L + j) * PLM_BWD_TS;
+    uint32_t *out = perm + ((int64_t)t * L + j) * PLM_BWD_CAP;
+    uint16_t *bs = bstart + ((int64_t)t * L + j) * PLM_BWD_BS;
+    const uint32_t zero_off = (uint32_t)(PLM_BWD_TS * S * sizeof(float));
     hist[lane] = 0;
     __syncwarp();
     for (int k = lane; k < cnt32; k += 32) {
         int c = 31;
         if (k < cnt) {
             c = codes[(base + k) * L + j];
-            if (c >= q) c = 31;            // ignored gap (or invalid) -> dropped bucket
+            if (c >= q) c = 31;            // ignored gap -> not listed
         }
         const unsigned m = __match_any_sync(0xffffffffu, c);
         if (lane == __ffs(m) - 1) hist[c] += __popc(m);
         __syncwarp();
     }
-    // exclusive scan over the 32 buckets (lane = bucket)
-    int v = hist[lane], incl = v;
+    // exclusive scan of the 8-aligned bucket sizes (lane = bucket); bucket 31 is dropped
+    const int v = (lane < q) ? ((hist[lane] + 7) & ~7) : 0;
+    int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int u = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += u;
     }
     __syncwarp();
-    hist[lane] = incl - v;
+    start[lane] = incl - v;
+    if (lane == 31) start[32] = incl;
+    __syncwarp();
+    if (lane <= q && lane < PLM_BWD_BS) bs[lane] = (uint16_t)start[lane < q ? lane : q];
+    if (lane == 0) bs[q] = (uint16_t)start[q];
+    // pad slots first (zero-row offset), then scatter the real entries
+    for (int b = 0; b < q; b++) {
+        const int s0 = start[b] + hist[b], s1 = start[b] + ((hist[b] + 7) & ~7);
+        for (int k = s0 + lane; k < s1; k += 32) out[k] = zero_off;
+    }
+    __syncwarp();
+    hist[lane] = start[lane];            // running write positions
     __syncwarp();
     for (int k = lane; k < cnt32; k += 32) {
         int c = 31;
@@ -121,14 +141,15 @@ __global__ void build_buckets_kernel(const uint8_t *__restrict__ codes, uint16_t
         __syncwarp();
         if (lane == __ffs(m) - 1) hist[c] += __popc(m);
         __syncwarp();
-        out[pos] = (uint16_t)((c << 11) | (k < cnt ? k : 0));
+        if (c < q) out[pos] = (uint32_t)(k * S * sizeof(float));
     }
 }
 
-int plm_build_buckets(const PlmGeom &g, const uint8_t *d_codes, uint16_t *d_perm, cudaStream_t st)
+int plm_build_buckets(const PlmGeom &g, const uint8_t *d_codes, uint32_t *d_perm, uint16_t *d_bstart,
+                      cudaStream_t st)
 {
     dim3 grid((unsigned)g.ntiles_b, (unsigned)g.L);
-    build_buckets_kernel<<<grid, 32, 0, st>>>(d_codes, d_perm, g.N, g.L, g.q);
+    build_buckets_kernel<<<grid, 32, 0, st>>>(d_codes, d_perm, d_bstart, g.N, g.L, g.q, g.S);
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -403,19 +424,18 @@ int plm_onehot_residual(const PlmGeom &g, const uint32_t *d_msa4, const float *d
 // ----------------------------------------------------------------------------------------------
 template <int S>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-plm_bwd_kernel(const float *__restrict__ R, const uint16_t *__restrict__ perm, float *__restrict__ G,
-               PlmGeom g)
+plm_bwd_kernel(const float *__restrict__ R, const uint32_t *__restrict__ perm,
+               const uint16_t *__restrict__ bstart, float *__restrict__ G, PlmGeom g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *Rs = reinterpret_cast<float *>(smem_raw);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)PLM_BWD_TS * S * sizeof(float));
+    float *Rs = reinterpret_cast<float *>(smem_raw);                       // [PLM_BWD_TS + 1][S]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(PLM_BWD_TS + 4) * S * sizeof(float));
 
     const int t = blockIdx.x, i = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)t * PLM_BWD_TS;
     const int cnt = (int)min((int64_t)PLM_BWD_TS, g.N - base);
     const int cnt4 = (cnt + 3) & ~3;
-    const int len8 = (cnt + 7) & ~7;
     const int Q = g.q;
     const int BLK = g.QB * S;
 
@@ -423,6 +443,7 @@ plm_bwd_kernel(const float *__restrict__ R, const uint16_t *__restrict__ perm, f
         mbar_init(bar, 1);
         mbar_fence_init();
     }
+    if (tid < S) Rs[PLM_BWD_TS * S + tid] = 0.f;          // the all-zero row that padding entries point at
     __syncthreads();
     if (tid == 0) {
         const uint32_t bytes = (uint32_t)((size_t)cnt4 * S * sizeof(float));
@@ -431,57 +452,49 @@ plm_bwd_kernel(const float *__restrict__ R, const uint16_t *__restrict__ perm, f
     }
     mbar_wait(bar, 0);
 
-    const bool act = lane < S;
-    const int la = act ? lane : 0;
+    const char *Rl = reinterpret_cast<const char *>(Rs + (lane < S ? lane : 0));
     for (int j = warp; j < g.L; j += BWD_THREADS / 32) {
         if (j == i) continue;
-        const uint16_t *list = perm + ((int64_t)t * g.L + j) * PLM_BWD_TS;
+        const uint32_t *list = perm + ((int64_t)t * g.L + j) * PLM_BWD_CAP;
+        const uint16_t *bs = bstart + ((int64_t)t * g.L + j) * PLM_BWD_BS;
         float *Gij = G + (int64_t)i * g.row_block() + (int64_t)j * BLK;
-        int cur = -1;
-        float acc = 0.f;
-        for (int k = 0; k < len8; k += 8) {
-            const uint4 e = __ldg(reinterpret_cast<const uint4 *>(list + k));
-            uint32_t ent[8];
-            ent[0] = e.x & 0xffffu; ent[1] = e.x >> 16;
-            ent[2] = e.y & 0xffffu; ent[3] = e.y >> 16;
-            ent[4] = e.z & 0xffffu; ent[5] = e.z >> 16;
-            ent[6] = e.w & 0xffffu; ent[7] = e.w >> 16;
-            const int bf = (int)(ent[0] >> 11), bl = (int)(ent[7] >> 11);
-            if (bf == 31) break;
-            if (bf == cur && bl == cur) {
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = Rs[(ent[u] & 2047u) * S + la];
-                acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-            } else {
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int b = (int)(ent[u] >> 11);
-                    if (b == 31) break;
-                    if (b != cur) {
-                        if (cur >= 0 && lane < Q) atomicAdd(Gij + cur * S + lane, acc);
-                        cur = b;
-                        acc = 0.f;
-                    }
-                    acc += Rs[(ent[u] & 2047u) * S + la];
-                }
+        const int my_start = (lane <= Q) ? (int)bs[lane] : 0;       // lane b holds bstart[b]
+        for (int b = 0; b < Q; b++) {
+            const int k0 = __shfl_sync(0xffffffffu, my_start, b);
+            const int k1 = __shfl_sync(0xffffffffu, my_start, b + 1);
+            if (k0 == k1) continue;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int k = k0; k < k1; k += 8) {
+                const uint4 e0 = __ldg(reinterpret_cast<const uint4 *>(list + k));
+                const uint4 e1 = __ldg(reinterpret_cast<const uint4 *>(list + k + 4));
+                const float v0 = *reinterpret_cast<const float *>(Rl + e0.x);
+                const float v1 = *reinterpret_cast<const float *>(Rl + e0.y);
+                const float v2 = *reinterpret_cast<const float *>(Rl + e0.z);
+                const float v3 = *reinterpret_cast<const float *>(Rl + e0.w);
+                const float v4 = *reinterpret_cast<const float *>(Rl + e1.x);
+                const float v5 = *reinterpret_cast<const float *>(Rl + e1.y);
+                const float v6 = *reinterpret_cast<const float *>(Rl + e1.z);
+                const float v7 = *reinterpret_cast<const float *>(Rl + e1.w);
+                acc0 += (v0 + v1) + (v2 + v3);
+                acc1 += (v4 + v5) + (v6 + v7);
             }
+            if (lane < Q) atomicAdd(Gij + b * S + lane, acc0 + acc1);
         }
-        if (cur >= 0 && lane < Q) atomicAdd(Gij + cur * S + lane, acc);
     }
 }
 
-int plm_backward(const PlmGeom &g, const float *d_R, const uint16_t *d_perm, float *d_G, cudaStream_t st)
+int plm_backward(const PlmGeom &g, const float *d_R, const uint32_t *d_perm, const uint16_t *d_bstart,
+                 float *d_G, cudaStream_t st)
 {
     dim3 grid((unsigned)g.ntiles_b, (unsigned)g.L);
     if (g.S == 21) {
-        const size_t smem = (size_t)PLM_BWD_TS * 21 * sizeof(float) + sizeof(uint64_t);
+        const size_t smem = (size_t)(PLM_BWD_TS + 4) * 21 * sizeof(float) + sizeof(uint64_t);
         EVC_CUDA(cudaFuncSetAttribute(plm_bwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        plm_bwd_kernel<21><<<grid, BWD_THREADS, smem, st>>>(d_R, d_perm, d_G, g);
+        plm_bwd_kernel<21><<<grid, BWD_THREADS, smem, st>>>(d_R, d_perm, d_bstart, d_G, g);
     } else if (g.S == 5) {
-        const size_t smem = (size_t)PLM_BWD_TS * 5 * sizeof(float) + sizeof(uint64_t);
-        plm_bwd_kernel<5><<<grid, BWD_THREADS, smem, st>>>(d_R, d_perm, d_G, g);
+        const size_t smem = (size_t)(PLM_BWD_TS + 4) * 5 * sizeof(float) + sizeof(uint64_t);
+        plm_bwd_kernel<5><<<grid, BWD_THREADS, smem, st>>>(d_R, d_perm, d_bstart, d_G, g);
     } else {
         set_error("plm_backward: unsupported row stride");
         return 1;

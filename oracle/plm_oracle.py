@@ -332,7 +332,7 @@ def initial_point(fi, L, q, n_eff):
 
 
 def fit(codes, w, q, lambda_h, lambda_J, gap_code=-1, x0=None, max_iter=2000,
-        gtol=1e-9):
+        gtol=1e-9, objective_fn=None):
     """Minimise the (strictly convex) objective in float64 with scipy's
     L-BFGS-B -- an implementation independent of the product's L-BFGS."""
     from scipy.optimize import minimize
@@ -342,7 +342,10 @@ def fit(codes, w, q, lambda_h, lambda_J, gap_code=-1, x0=None, max_iter=2000,
         x0 = np.zeros(n)
 
     def fun(x):
-        fx, g, _ = objective(x, codes, w, q, lambda_h, lambda_J, gap_code)
+        if objective_fn is not None:       # e.g. the C/OpenMP float64 port (same objective, faster)
+            fx, g, _ = objective_fn(x)
+        else:
+            fx, g, _ = objective(x, codes, w, q, lambda_h, lambda_J, gap_code)
         return fx, g
 
     res = minimize(fun, x0, jac=True, method="L-BFGS-B",

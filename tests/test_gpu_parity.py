@@ -295,7 +295,8 @@ def test_run_plmc_config1_vs_oracle_optimum(engine, tmp_path, ignore_gaps):
     assert np.array_equal(run.counts, counts_o)
     w = 1.0 / counts_o
     xo, info = po.fit(ali.codes, w, q, 0.01, lam_J, ali.gap_code, x0=tools.initial_point(
-        po.frequencies(ali.codes, w, q, ali.gap_code)[0], w.sum(), L, q).astype(np.float64), max_iter=4000)
+        po.frequencies(ali.codes, w, q, ali.gap_code)[0], w.sum(), L, q).astype(np.float64), max_iter=4000,
+        objective_fn=lambda v: co.plm_eval(ali.codes, w, v, q, 0.01, lam_J, "f64"))
     m = po.read_model(str(tmp_path / "o.model"))
     x = np.concatenate([m["h"].ravel(), m["J"].ravel()]).astype(np.float64)
     cn = np.loadtxt(str(tmp_path / "o_ECs.txt"), usecols=5)
