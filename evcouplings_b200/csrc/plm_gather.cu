@@ -46,7 +46,7 @@ namespace evc {
 
 constexpr int FWD_JC = 24;        // sites per streamed chunk of W[i]
 constexpr int FWD_THREADS = 256;
-constexpr int BWD_THREADS = 512;
+constexpr int BWD_THREADS = 1024;
 
 bool plm_supported_q(int q) { return q == 21 || q == 20 || q == 5 || q == 4; }
 
@@ -430,6 +430,7 @@ plm_bwd_kernel(const float *__restrict__ R, const uint32_t *__restrict__ perm,
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *Rs = reinterpret_cast<float *>(smem_raw);                       // [PLM_BWD_TS + 1][S]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(PLM_BWD_TS + 4) * S * sizeof(float));
+    int *s_next = reinterpret_cast<int *>(bar + 1);                        // dynamic column scheduler
 
     const int t = blockIdx.x, i = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -442,6 +443,7 @@ plm_bwd_kernel(const float *__restrict__ R, const uint32_t *__restrict__ perm,
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
+        *s_next = BWD_THREADS / 32;
     }
     if (tid < S) Rs[PLM_BWD_TS * S + tid] = 0.f;          // the all-zero row that padding entries point at
     __syncthreads();
@@ -453,8 +455,13 @@ plm_bwd_kernel(const float *__restrict__ R, const uint32_t *__restrict__ perm,
     mbar_wait(bar, 0);
 
     const char *Rl = reinterpret_cast<const char *>(Rs + (lane < S ? lane : 0));
-    for (int j = warp; j < g.L; j += BWD_THREADS / 32) {
-        if (j == i) continue;
+    for (int j = warp; j < g.L;) {
+        if (j == i) {
+            int nj = 0;
+            if (lane == 0) nj = atomicAdd(s_next, 1);
+            j = __shfl_sync(0xffffffffu, nj, 0);
+            continue;
+        }
         const uint32_t *list = perm + ((int64_t)t * g.L + j) * PLM_BWD_CAP;
         const uint16_t *bs = bstart + ((int64_t)t * g.L + j) * PLM_BWD_BS;
         float *Gij = G + (int64_t)i * g.row_block() + (int64_t)j * BLK;
@@ -480,6 +487,9 @@ plm_bwd_kernel(const float *__restrict__ R, const uint32_t *__restrict__ perm,
             }
             if (lane < Q) atomicAdd(Gij + b * S + lane, acc0 + acc1);
         }
+        int nj = 0;
+        if (lane == 0) nj = atomicAdd(s_next, 1);      // next unclaimed column
+        j = __shfl_sync(0xffffffffu, nj, 0);
     }
 }
 
@@ -488,12 +498,12 @@ int plm_backward(const PlmGeom &g, const float *d_R, const uint32_t *d_perm, con
 {
     dim3 grid((unsigned)g.ntiles_b, (unsigned)g.L);
     if (g.S == 21) {
-        const size_t smem = (size_t)(PLM_BWD_TS + 4) * 21 * sizeof(float) + sizeof(uint64_t);
+        const size_t smem = (size_t)(PLM_BWD_TS + 4) * 21 * sizeof(float) + 2 * sizeof(uint64_t);
         EVC_CUDA(cudaFuncSetAttribute(plm_bwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         plm_bwd_kernel<21><<<grid, BWD_THREADS, smem, st>>>(d_R, d_perm, d_bstart, d_G, g);
     } else if (g.S == 5) {
-        const size_t smem = (size_t)(PLM_BWD_TS + 4) * 5 * sizeof(float) + sizeof(uint64_t);
+        const size_t smem = (size_t)(PLM_BWD_TS + 4) * 5 * sizeof(float) + 2 * sizeof(uint64_t);
         plm_bwd_kernel<5><<<grid, BWD_THREADS, smem, st>>>(d_R, d_perm, d_bstart, d_G, g);
     } else {
         set_error("plm_backward: unsupported row stride");
