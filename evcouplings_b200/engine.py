@@ -24,11 +24,7 @@ def _torch():
     return torch
 
 
-def shard_bounds(n, world, rank):
-    """Contiguous block partition of n items over `world` ranks (sizes differ by <= 1)."""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+from .dist import Collective, shard_bounds   # noqa: E402,F401
 
 
 class CudaEngine(object):
@@ -38,14 +34,8 @@ class CudaEngine(object):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.EngineUnavailableError("torch sees no CUDA device; the PLM engine has no CPU fallback")
-        import torch.distributed as dist
-        self.dist = dist
-        self.group = group
-        if dist.is_available() and dist.is_initialized():
-            self.rank = dist.get_rank(group)
-            self.world = dist.get_world_size(group)
-        else:
-            self.rank, self.world = 0, 1
+        self.coll = Collective(group)
+        self.rank, self.world = self.coll.rank, self.coll.world
         if device is None:
             device = torch.cuda.current_device()
         self.device_index = int(device)
@@ -58,8 +48,7 @@ class CudaEngine(object):
         return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
     def all_reduce(self, tensor):
-        if self.world > 1:
-            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.coll.all_reduce_sum(tensor)
 
     @staticmethod
     def ptr(t):

@@ -1,0 +1,120 @@
+"""
+N > 1 path on CPU: world_size-2 gloo process group (127.0.0.1), exercising the product's sharding /
+collective plumbing (evcouplings_b200.dist) and the L-BFGS host logic in lock-step on two ranks.  The
+numerical backend is the test-only oracle (tests/cpu_engine.py).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from evcouplings_b200 import lbfgs
+    from evcouplings_b200.dist import Collective, shard_bounds, hamming_tile_coords
+    from oracle import c_oracle as co
+    from oracle import plm_oracle as po
+    from cpu_engine import OracleProblem
+
+    coll = Collective()
+    assert (coll.rank, coll.world) == (rank, world)
+    N, L, q = 301, 9, 21
+    codes = po.synthetic_msa_codes(N, L, 5)
+
+    # (b) Hamming: contiguous ranges of upper-triangular 128x128 tiles per rank, all-reduce of int32 counters
+    T = (N + 127) // 128
+    ntiles = T * (T + 1) // 2
+    lo, hi = shard_bounds(ntiles, world, rank)
+    thr = po.identity_threshold_count(0.8, L)
+    counts = np.zeros(N, dtype=np.int32)
+    for idx in range(lo, hi):
+        R, C = hamming_tile_coords(idx, T)
+        r0, r1, c0, c1 = R * 128, min(N, R * 128 + 128), C * 128, min(N, C * 128 + 128)
+        ident = (codes[r0:r1, None, :] == codes[None, c0:c1, :]).sum(axis=2) >= thr
+        counts[r0:r1] += ident.sum(axis=1)
+        if R != C:
+            counts[c0:c1] += ident.sum(axis=0)
+    tc = torch.from_numpy(counts)
+    coll.all_reduce_sum(tc)
+    full = co.hamming_counts(codes, thr)
+    assert np.array_equal(tc.numpy(), full)
+    w = 1.0 / full
+
+    # (a) PLM: sequence shards, one all-reduce of [g] and of -loglk per evaluation, regulariser after
+    class ShardedProblem(OracleProblem):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            s0, s1 = shard_bounds(N, world, rank)
+            self.c_loc, self.w_loc = self.codes[s0:s1], self.w[s0:s1]
+
+        def evaluate(self, x):
+            nll, g, _ = co.plm_eval(self.c_loc, self.w_loc, x, self.q, 0.0, 0.0, precision="f64")
+            tg = torch.from_numpy(g)
+            tf = torch.tensor([nll], dtype=torch.float64)
+            coll.all_reduce_sum(tg)
+            coll.all_reduce_sum(tf)
+            nh = self.L * self.q
+            lam = np.concatenate([np.full(nh, self.lambda_h), np.full(self.n - nh, self.lambda_J)])
+            self.g[:] = tg.numpy() + 2 * lam * x
+            self.last_negloglk = float(tf.item())
+            self.evaluations += 1
+            return float(tf.item()) + float((lam * x * x).sum())
+
+    prob = ShardedProblem(codes, w, q, -1, 0.01, 0.3, m=6)
+    res = prob.fit(np.zeros(prob.n), lbfgs.default_params(max_iterations=25, epsilon=1e-9))
+    # lock-step: both ranks hold bit-identical parameters and took identical decisions
+    tx = torch.from_numpy(prob.x.copy())
+    gathered = [torch.zeros_like(tx) for _ in range(world)]
+    dist.all_gather(gathered, tx)
+    assert all(torch.equal(gathered[0], t) for t in gathered)
+    np.save(os.path.join(out_dir, "x_rank%d.npy" % rank), prob.x)
+    with open(os.path.join(out_dir, "status_rank%d.txt" % rank), "w") as f:
+        f.write("%s %d %d" % (res.status, res.iterations, res.evaluations))
+    coll.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_lockstep(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    x0 = np.load(tmp_path / "x_rank0.npy")
+    x1 = np.load(tmp_path / "x_rank1.npy")
+    assert np.array_equal(x0, x1)
+    s0 = open(tmp_path / "status_rank0.txt").read()
+    assert s0 == open(tmp_path / "status_rank1.txt").read()
+    assert s0.startswith("LBFGSERR_MAXIMUMITERATION 25")
+    # same answer as the single-process run of the same algorithm (shards sum to the whole)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpu_engine import OracleProblem
+    from evcouplings_b200 import lbfgs
+    from oracle import c_oracle as co, plm_oracle as po
+    codes = po.synthetic_msa_codes(301, 9, 5)
+    w = 1.0 / co.hamming_counts(codes, po.identity_threshold_count(0.8, 9))
+    single = OracleProblem(codes, w, 21, -1, 0.01, 0.3, m=6)
+    single.fit(np.zeros(single.n), lbfgs.default_params(max_iterations=25, epsilon=1e-9))
+    assert np.abs(single.x - x0).max() < 1e-9
+
+
+def test_tile_coords_cover_triangle_once():
+    from evcouplings_b200.dist import hamming_tile_coords, shard_bounds
+    for T in (1, 2, 5, 13):
+        n = T * (T + 1) // 2
+        seen = [hamming_tile_coords(k, T) for k in range(n)]
+        assert seen == [(r, c) for r in range(T) for c in range(r, T)]
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = shard_bounds(n, world, r)
+                cover += list(range(lo, hi))
+            assert cover == list(range(n))

@@ -1,0 +1,110 @@
+"""
+Drop-in boundary test (CPU, this container only): the reference's OWN couplings protocol
+(evcouplings/couplings/protocol.py:363-429 ``standard`` -> ``infer_plmc`` :56-257) runs unmodified with
+``evcouplings.couplings.tools.run_plmc`` replaced by ``evcouplings_b200.run_plmc``; the reference's own
+readers (CouplingsModel model.py:317-400, read_raw_ec_file pairs.py:34-65, parse_plmc_log tools.py:20-108)
+consume what we write.  The numerical engine injected here is the test-only oracle engine (no GPU in this
+container); the same host code runs over the CUDA engine in tests/test_gpu_parity.py.
+Skipped where /root/reference does not exist (the GPU box).
+"""
+import functools
+import os
+
+import numpy as np
+import pytest
+
+import ref_harness
+
+pytestmark = pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    ref_harness.install()
+    import evcouplings.couplings.tools as ct
+    import evcouplings.couplings.protocol as cpr
+    import evcouplings.couplings.model as cm
+    import evcouplings.couplings.pairs as cp
+    return dict(ct=ct, cpr=cpr, cm=cm, cp=cp)
+
+
+def _kwargs(prefix, a2m, L, ignore_gaps):
+    return dict(
+        protocol="standard", prefix=prefix, alignment_file=a2m, focus_mode=True, focus_sequence="seq0/1-%d" % L,
+        theta=0.8, alphabet=None, segments=[["A_1", "aa", "seq0", 1, L, list(range(1, L + 1))]],
+        ignore_gaps=ignore_gaps, iterations=30, lambda_h=0.01, lambda_J=0.01, lambda_J_times_Lq=True,
+        lambda_group=None, scale_clusters=None, cpu=2, plmc="plmc", reuse_ecs=False, min_sequence_distance=6,
+        frequencies_file=None, scoring_model="skewnormal",
+    )
+
+
+@pytest.mark.parametrize("ignore_gaps", [True, False])
+def test_reference_standard_protocol_over_our_run_plmc(ref, tmp_path, ignore_gaps):
+    from evcouplings_b200 import synthetic, tools
+    from cpu_engine import OracleEngine
+    from oracle import plm_oracle as po
+    N, L = 200, 40                      # BASELINE configs[0]
+    codes = synthetic.synthetic_msa_codes(N, L, 1)
+    a2m = str(tmp_path / "cfg1.a2m")
+    synthetic.write_a2m(a2m, codes)
+    captured = {}
+
+    def run_plmc(*args, **kwargs):
+        res, run = tools.run_plmc(*args, engine=OracleEngine(), return_run=True, **kwargs)
+        captured["run"], captured["kwargs"], captured["args"] = run, kwargs, args
+        return res
+
+    ct = ref["ct"]
+    original = ct.run_plmc
+    ct.run_plmc = run_plmc
+    try:
+        prefix = str(tmp_path / "out" / "job")
+        outcfg = ref["cpr"].run(**_kwargs(prefix, a2m, L, ignore_gaps))
+    finally:
+        ct.run_plmc = original
+
+    # the protocol handed us lambda_J already scaled by (q_eff - 1) * (L - 1)   (protocol.py:157-179)
+    q_eff = 20 if ignore_gaps else 21
+    assert abs(captured["kwargs"]["lambda_J"] - 0.01 * (q_eff - 1) * (L - 1)) < 1e-12
+    assert captured["kwargs"]["focus_seq"] == "seq0/1-40" and captured["kwargs"]["theta"] == 0.8
+
+    # stage outputs the rest of the pipeline consumes
+    for key in ("model_file", "raw_ec_file", "ec_file"):
+        assert os.path.getsize(outcfg[key]) > 0
+    assert outcfg["num_sites"] == L and outcfg["num_valid_sequences"] == N
+    assert abs(outcfg["effective_sequences"] - captured["run"].n_eff) < 0.06
+    assert outcfg["region_start"] == 1
+    assert os.path.exists(prefix + "_iteration_table.csv")
+    assert os.path.exists(prefix + ".couplings_standard_plmc.outcfg")     # restart record (YAML of PlmcResult)
+
+    # the reference's own readers on our files
+    model = ref["cm"].CouplingsModel(outcfg["model_file"])
+    run = captured["run"]
+    assert model.L == L and model.num_symbols == q_eff and model.N_valid == N
+    assert "".join(model.alphabet) == ("ACDEFGHIKLMNPQRSTVWY" if ignore_gaps else "-ACDEFGHIKLMNPQRSTVWY")
+    h = run.x[:L * q_eff].reshape(L, q_eff)
+    assert np.allclose(model.h_i, h, atol=0, rtol=0)
+    iu, ju = np.triu_indices(L, 1)
+    J = run.x[L * q_eff:].reshape(-1, q_eff, q_eff)
+    assert np.array_equal(model.J_ij[iu, ju], J.astype(np.float64))
+    assert np.array_equal(model.J_ij[ju, iu], J.transpose(0, 2, 1).astype(np.float64))
+    assert abs(model.theta - 0.2) < 1e-7 and abs(model.N_eff - run.n_eff) < 1e-2
+    assert "".join(model.target_seq) == run.alignment.target_seq
+    ecs = ref["cp"].read_raw_ec_file(outcfg["raw_ec_file"], sort=False)
+    assert len(ecs) == L * (L - 1) // 2
+    assert np.abs(ecs["cn"].values - po.cn_scores(J, L)).max() < 1e-6
+    # the reference's own log parser accepts our log and agrees with ours
+    it_ref, fields_ref = ct.parse_plmc_log(run.log)
+    it_own, fields_own = tools.parse_plmc_log(run.log)
+    assert fields_ref == fields_own
+    assert list(it_ref.columns) == list(it_own.columns) and len(it_ref) == len(it_own) == 30
+    assert it_ref.equals(it_own)
+
+
+def test_reference_parse_of_realistic_failure_modes(ref):
+    """mandatory log lines: the reference raises KeyError without them (tools.py:97-99); ours too."""
+    from evcouplings_b200 import tools
+    with pytest.raises(KeyError):
+        ref["ct"].parse_plmc_log("nothing useful")
+    with pytest.raises(KeyError):
+        tools.parse_plmc_log("nothing useful")
