@@ -2,6 +2,8 @@
 // reference's plmc call site (evcouplings/couplings/tools.py:202-266) talks to.
 #include "../../include/evcplm.h"
 
+#include <stdlib.h>
+
 #include <new>
 #include <string>
 #include <vector>
@@ -32,6 +34,14 @@ struct evc_plm {
     float *d_x_tmp = nullptr;       // host-buffer convenience path
     float *d_g_tmp = nullptr;
     double *d_fx_tmp = nullptr;
+    // tensor-core backward (plm_tc.cu); allocated on first use
+    int bwd_mode = 0;               // 0 = gather/bucket kernel, 1 = tcgen05 GEMM
+    PlmTcGeom tc{};
+    void *d_xt = nullptr;
+    void *d_rt_hi = nullptr;
+    void *d_rt_lo = nullptr;
+    float *d_Gd = nullptr;
+    void *tc_maps = nullptr;        // host: 3 CUtensorMap
     bool profiling = false;         // record CUDA events around the stages of evc_plm_eval_data
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -141,6 +151,11 @@ void evc_plm_destroy(evc_plm_t *h)
     cudaFree(h->d_x_tmp);
     cudaFree(h->d_g_tmp);
     cudaFree(h->d_fx_tmp);
+    cudaFree(h->d_xt);
+    cudaFree(h->d_rt_hi);
+    cudaFree(h->d_rt_lo);
+    cudaFree(h->d_Gd);
+    free(h->tc_maps);
     for (int k = 0; k < 5; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     delete h;
@@ -222,20 +237,59 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
     cudaStream_t st = as_stream(stream);
     const PlmGeom &g = h->g;
     const bool prof = h->profiling;
+    const bool tc = h->bwd_mode == 1;
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[0], st));
     if (plm_expand(g, d_x, h->d_W, st)) return 1;
-    EVC_CUDA(cudaMemsetAsync(h->d_G, 0, (size_t)g.w_floats() * sizeof(float), st));
+    if (!tc) EVC_CUDA(cudaMemsetAsync(h->d_G, 0, (size_t)g.w_floats() * sizeof(float), st));
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
-    if (plm_forward(g, h->d_W, d_x, h->d_msa4, h->d_wts, h->d_R, h->d_gh_part, h->d_fx_part, st)) return 1;
-    if (prof) EVC_CUDA(cudaEventRecord(h->ev[2], st));
-    if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
-    if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
-    if (plm_finalize(g, h->d_G, h->d_gh_part, h->d_fx_part, d_g, d_g + (int64_t)g.L * g.q, d_fx, 1.0f, st))
+    if (plm_forward(g, h->d_W, d_x, h->d_msa4, h->d_wts, h->d_R, tc ? h->d_rt_hi : nullptr,
+                    tc ? h->d_rt_lo : nullptr, h->tc.Kp, h->d_gh_part, h->d_fx_part, st))
         return 1;
+    if (prof) EVC_CUDA(cudaEventRecord(h->ev[2], st));
+    if (tc) {
+        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
+        if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, d_g + (int64_t)g.L * g.q, 1.0f, st)) return 1;
+        if (plm_finalize_fields(g, h->d_gh_part, h->d_fx_part, d_g, d_fx, st)) return 1;
+    } else {
+        if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
+        if (plm_finalize(g, h->d_G, h->d_gh_part, h->d_fx_part, d_g, d_g + (int64_t)g.L * g.q, d_fx, 1.0f, st))
+            return 1;
+    }
     if (prof) {
         EVC_CUDA(cudaEventRecord(h->ev[4], st));
         h->ev_valid = true;
     }
+    return 0;
+}
+
+int evc_plm_set_backward(evc_plm_t *h, int32_t mode)
+{
+    if (!h) { set_error("evc_plm_set_backward: null handle"); return 1; }
+    if (mode != 0 && mode != 1) { set_error("evc_plm_set_backward: mode must be 0 (gather) or 1 (tensor core)"); return 1; }
+    EVC_CUDA(cudaSetDevice(h->device));
+    if (mode == 1 && !h->d_xt) {
+        plm_tc_geometry(h->g, h->tc);
+        const PlmTcGeom &t = h->tc;
+        const size_t xb = (size_t)t.Mp * t.Kp * 2, rb = (size_t)t.Np * t.Kp * 2;
+        if (cudaMalloc(&h->d_xt, xb) != cudaSuccess || cudaMalloc(&h->d_rt_hi, rb) != cudaSuccess ||
+            cudaMalloc(&h->d_rt_lo, rb) != cudaSuccess ||
+            cudaMalloc(&h->d_Gd, (size_t)t.Mp * t.Np * sizeof(float)) != cudaSuccess) {
+            set_error(std::string("evc_plm_set_backward: device allocation failed: ") +
+                      cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        EVC_CUDA(cudaMemset(h->d_rt_hi, 0, rb));
+        EVC_CUDA(cudaMemset(h->d_rt_lo, 0, rb));
+        EVC_CUDA(cudaMemset(h->d_Gd, 0, (size_t)t.Mp * t.Np * sizeof(float)));
+        if (plm_tc_build_xt(h->g, t, h->d_msa4, h->d_xt, 0)) return 1;
+        EVC_CUDA(cudaDeviceSynchronize());
+        h->tc_maps = aligned_alloc(64, round_up((int64_t)plm_tc_map_bytes(), 64));
+        if (!h->tc_maps) { set_error("evc_plm_set_backward: out of host memory"); return 1; }
+        if (plm_tc_make_maps(t, h->d_xt, h->d_rt_hi, h->d_rt_lo, h->tc_maps)) return 1;
+    }
+    h->bwd_mode = mode;
     return 0;
 }
 

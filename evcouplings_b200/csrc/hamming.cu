@@ -60,7 +60,7 @@ __device__ __forceinline__ void tile_from_index(int64_t idx, int64_t T, int64_t 
     C = r + (idx - (r * T - r * (r - 1) / 2));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int thr,
                     int64_t tile_begin, int64_t T, int *__restrict__ counts)
 {

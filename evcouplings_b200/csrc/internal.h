@@ -43,7 +43,8 @@ int plm_build_buckets(const PlmGeom &g, const uint8_t *d_codes, uint32_t *d_perm
                       cudaStream_t st);
 int plm_expand(const PlmGeom &g, const float *d_x, float *d_W, cudaStream_t st);
 int plm_forward(const PlmGeom &g, const float *d_W, const float *d_x, const uint32_t *d_msa4,
-                const float *d_wts, float *d_R, float *d_gh_part, double *d_fx_part, cudaStream_t st);
+                const float *d_wts, float *d_R, void *d_rt_hi, void *d_rt_lo, int64_t Kp, float *d_gh_part,
+                double *d_fx_part, cudaStream_t st);
 int plm_onehot_residual(const PlmGeom &g, const uint32_t *d_msa4, const float *d_wts, float *d_R,
                         float *d_gh_part, cudaStream_t st);
 int plm_backward(const PlmGeom &g, const float *d_R, const uint32_t *d_perm, const uint16_t *d_bstart,
@@ -52,6 +53,22 @@ int plm_finalize(const PlmGeom &g, const float *d_G, const float *d_gh_part, con
                  float *d_gh, float *d_gJ, double *d_fx, float scale_pair, cudaStream_t st);
 int plm_add_reg(const PlmGeom &g, const float *d_x, float *d_g, double *d_fx, float lambda_h,
                 float lambda_J, cudaStream_t st);
+
+// plm_tc.cu -- backward as a bf16 tcgen05 GEMM (dense one-hot contraction)
+struct PlmTcGeom {
+    int64_t Mp;   // L*q rounded up to the 128-row MMA tile  (rows of Xt, Gd)
+    int64_t Np;   // L*q rounded up to the 192-column tile   (rows of Rt_hi / Rt_lo, columns of Gd)
+    int64_t Kp;   // sequences rounded up to the 64-wide K block
+};
+void plm_tc_geometry(const PlmGeom &g, PlmTcGeom &t);
+size_t plm_tc_map_bytes();
+int plm_tc_build_xt(const PlmGeom &g, const PlmTcGeom &t, const uint32_t *d_msa4, void *d_xt, cudaStream_t st);
+int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_lo, void *maps_out_host);
+int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps_host, float *d_Gd, cudaStream_t st);
+int plm_tc_finalize_pairs(const PlmGeom &g, const PlmTcGeom &t, const float *d_Gd, float *d_gJ, float scale,
+                          cudaStream_t st);
+int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
+                        double *d_fx, cudaStream_t st);
 
 // vecops.cu
 int vec_dot(const float *a, const float *b, int64_t n, double *out, cudaStream_t st);

@@ -39,6 +39,8 @@
 // Bound: on-chip.  Per cell-op (n,i,j,a) the path does one 4-byte shared-memory read
 // in forward and one in backward; compulsory HBM traffic is ~1.9 GB / evaluation at
 // N=50k, L=200 (R write+read, W, G), i.e. <1 ms of the measured 6.5 TB/s.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -194,8 +196,8 @@ template <int Q, int S>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 plm_fwd_kernel(const float *__restrict__ W, const float *__restrict__ h,
                const uint32_t *__restrict__ msa4, const float *__restrict__ wts,
-               float *__restrict__ R, float *__restrict__ gh_part, double *__restrict__ fx_part,
-               PlmGeom g)
+               float *__restrict__ R, __nv_bfloat16 *__restrict__ Rt_hi, __nv_bfloat16 *__restrict__ Rt_lo,
+               int64_t Kp, float *__restrict__ gh_part, double *__restrict__ fx_part, PlmGeom g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int BLK = g.QB * S;
@@ -311,15 +313,33 @@ plm_fwd_kernel(const float *__restrict__ W, const float *__restrict__ h,
         z0[a] = z0[a] * inv0 - (a == si0 ? w0 : 0.f);
         z1[a] = z1[a] * inv1 - (a == si1 ? w1 : 0.f);
     }
-    if (n0 < N) {
-        float *r = R + ((int64_t)i * g.Nr + n0) * S;
+    if (Rt_hi != nullptr) {
+        // tensor-core backward: residuals transposed (sequence index fastest => coalesced), split in two bf16
 #pragma unroll
-        for (int a = 0; a < S; a++) r[a] = a < Q ? z0[a < Q ? a : 0] : 0.f;
-    }
-    if (n1 < N) {
-        float *r = R + ((int64_t)i * g.Nr + n1) * S;
+        for (int a = 0; a < Q; a++) {
+            const int64_t rowoff = ((int64_t)i * Q + a) * Kp;
+            if (n0 < N) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(z0[a]);
+                Rt_hi[rowoff + n0] = hi;
+                Rt_lo[rowoff + n0] = __float2bfloat16_rn(z0[a] - __bfloat162float(hi));
+            }
+            if (n1 < N) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(z1[a]);
+                Rt_hi[rowoff + n1] = hi;
+                Rt_lo[rowoff + n1] = __float2bfloat16_rn(z1[a] - __bfloat162float(hi));
+            }
+        }
+    } else {
+        if (n0 < N) {
+            float *r = R + ((int64_t)i * g.Nr + n0) * S;
 #pragma unroll
-        for (int a = 0; a < S; a++) r[a] = a < Q ? z1[a < Q ? a : 0] : 0.f;
+            for (int a = 0; a < S; a++) r[a] = a < Q ? z0[a < Q ? a : 0] : 0.f;
+        }
+        if (n1 < N) {
+            float *r = R + ((int64_t)i * g.Nr + n1) * S;
+#pragma unroll
+            for (int a = 0; a < S; a++) r[a] = a < Q ? z1[a < Q ? a : 0] : 0.f;
+        }
     }
     // deterministic CTA reduction of g_h and fx
 #pragma unroll
@@ -351,26 +371,34 @@ static size_t fwd_smem_bytes(const PlmGeom &g)
 
 template <int Q, int S>
 static int launch_fwd(const PlmGeom &g, const float *W, const float *x, const uint32_t *msa4,
-                      const float *wts, float *R, float *gh_part, double *fx_part, cudaStream_t st)
+                      const float *wts, float *R, void *rt_hi, void *rt_lo, int64_t Kp, float *gh_part,
+                      double *fx_part, cudaStream_t st)
 {
     const size_t smem = fwd_smem_bytes(g);
     EVC_CUDA(cudaFuncSetAttribute(plm_fwd_kernel<Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     dim3 grid((unsigned)g.ntiles_f, (unsigned)g.L);
-    plm_fwd_kernel<Q, S><<<grid, FWD_THREADS, smem, st>>>(W, x, msa4, wts, R, gh_part, fx_part, g);
+    plm_fwd_kernel<Q, S><<<grid, FWD_THREADS, smem, st>>>(W, x, msa4, wts, R,
+                                                          reinterpret_cast<__nv_bfloat16 *>(rt_hi),
+                                                          reinterpret_cast<__nv_bfloat16 *>(rt_lo), Kp, gh_part,
+                                                          fx_part, g);
     EVC_KERNEL_CHECK();
     return 0;
 }
 
 int plm_forward(const PlmGeom &g, const float *d_W, const float *d_x, const uint32_t *d_msa4,
-                const float *d_wts, float *d_R, float *d_gh_part, double *d_fx_part, cudaStream_t st)
+                const float *d_wts, float *d_R, void *d_rt_hi, void *d_rt_lo, int64_t Kp, float *d_gh_part,
+                double *d_fx_part, cudaStream_t st)
 {
+#define EVC_FWD(QQ, SS) \
+    return launch_fwd<QQ, SS>(g, d_W, d_x, d_msa4, d_wts, d_R, d_rt_hi, d_rt_lo, Kp, d_gh_part, d_fx_part, st)
     switch (g.q) {
-        case 21: return launch_fwd<21, 21>(g, d_W, d_x, d_msa4, d_wts, d_R, d_gh_part, d_fx_part, st);
-        case 20: return launch_fwd<20, 21>(g, d_W, d_x, d_msa4, d_wts, d_R, d_gh_part, d_fx_part, st);
-        case 5: return launch_fwd<5, 5>(g, d_W, d_x, d_msa4, d_wts, d_R, d_gh_part, d_fx_part, st);
-        case 4: return launch_fwd<4, 5>(g, d_W, d_x, d_msa4, d_wts, d_R, d_gh_part, d_fx_part, st);
+        case 21: EVC_FWD(21, 21);
+        case 20: EVC_FWD(20, 21);
+        case 5: EVC_FWD(5, 5);
+        case 4: EVC_FWD(4, 5);
     }
+#undef EVC_FWD
     set_error("plm_forward: unsupported number of states q=" + std::to_string(g.q));
     return 1;
 }
@@ -608,6 +636,14 @@ __global__ void add_reg_final_kernel(const double *__restrict__ partial, int nbl
 }
 
 double *reduction_scratch(int nd);   // vecops.cu
+
+int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
+                        double *d_fx, cudaStream_t st)
+{
+    finalize_fields_kernel<<<1, 256, 0, st>>>(d_gh_part, d_fx_part, d_gh, d_fx, g.L, g.q, g.S, g.ntiles_f);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
 
 int plm_add_reg(const PlmGeom &g, const float *d_x, float *d_g, double *d_fx, float lambda_h,
                 float lambda_J, cudaStream_t st)

@@ -1,0 +1,331 @@
+// Hot path (a), backward as a dense one-hot contraction on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// The north star allows tensor cores for the PLL gradient only if the dense recast beats the gather path
+// under ncu; bench.py / profiles/ carry that comparison (the gather backward is kept, see plm_gather.cu).
+//
+// Maths.  With X[n,(j,b)] = [s_nj = b] (one-hot, exact in bf16) and the residuals R[n,(i,a)] = r_ni(a),
+//     Gd[(j,b),(i,a)] = sum_n X[n,(j,b)] * R[n,(i,a)]                      (an (Lq x N) x (N x Lq) GEMM)
+//     g_J(i<j)[a][b]  = Gd[(j,b),(i,a)] + Gd[(i,a),(j,b)]
+// R is split R = R_hi + R_lo with both parts bf16 (hi = rn(r), lo = rn(r - hi)): 16 mantissa bits, relative
+// error 2^-17 per term -- below the fp32 accumulation noise of the sum over ~N/q terms -- and the two
+// products accumulate into the SAME fp32 TMEM accumulator.
+//
+// Operands (all K-major = sequence index fastest, so the forward kernel writes R^T coalesced):
+//     Xt    [Mp][Kp] bf16   static per MSA           (Mp = Lq rounded to 128, Kp = N rounded to 64)
+//     Rt_hi [Np][Kp] bf16   written by plm_fwd       (Np = Lq rounded to 192)
+//     Rt_lo [Np][Kp] bf16
+//     Gd    [Mp][Np] fp32
+// Kernel: one CTA per 128 x 192 output tile, K loop over all sequences in blocks of 64.
+//     warp 0 (1 thread)  TMA producer: cp.async.bulk.tensor 2-D, SWIZZLE_128B, 3-stage smem ring
+//                        (A 16 KB + B_hi 24 KB + B_lo 24 KB per stage), mbarrier expect_tx
+//     warp 1 (1 thread)  MMA issuer: 4 x 2 tcgen05.mma.cta_group::1.kind::f16 (M128 N192 K16) per stage,
+//                        tcgen05.commit -> "empty" barrier of the stage; final commit -> accumulator ready
+//     warp 2             TMEM allocator (256 columns)
+//     warps 4..7         epilogue: tcgen05.ld 32x32b.x32 -> registers -> Gd
+// Roofline: tensor pipe.  2 * 2 * Lq^2 * N flop per evaluation (7.1e12 at N=50k, L=200, q=21).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace evc {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 192;
+constexpr int TC_BK = 64;
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16384
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;        // 24576
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;   // 65536
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_THREADS = 256;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
+{
+    // spin with a cap so that a programming error becomes a trap instead of a hung GPU
+    uint32_t done = 0;
+    for (uint64_t it = 0; it < (1ull << 31); it++) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K-major, 128-byte swizzle, densely packed 8-row x 128-byte atoms (SBO = 1024 B), sm_100 descriptor version 1
+__device__ __forceinline__ uint64_t make_desc_sw128(const void *smem_ptr)
+{
+    const uint32_t addr = smem_u32(smem_ptr);
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);       // start address >> 4          bits [0,14)
+    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major) bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset >> 4      bits [32,46)
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                      // layout type SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = TC_BN
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+plm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
+                  const __grid_constant__ CUtensorMap tm_blo, float *__restrict__ Gd, int Np, int num_kb)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte alignment required by SWIZZLE_128B
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                                            ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *acc_ready = empty + TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+            mbar_wait_bounded(&empty[s], ph ^ 1u);
+            unsigned char *st = smem + s * TC_STAGE_BYTES;
+            mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+            tma_load_2d(st, &tm_a, kb * TC_BK, m_tile * TC_BM, &full[s]);
+            tma_load_2d(st + TC_A_BYTES, &tm_bhi, kb * TC_BK, n_tile * TC_BN, &full[s]);
+            tma_load_2d(st + TC_A_BYTES + TC_B_BYTES, &tm_blo, kb * TC_BK, n_tile * TC_BN, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+            mbar_wait_bounded(&full[s], ph);
+            tc_fence_after();
+            unsigned char *st = smem + s * TC_STAGE_BYTES;
+            const uint64_t da = make_desc_sw128(st);
+            const uint64_t dh = make_desc_sw128(st + TC_A_BYTES);
+            const uint64_t dl = make_desc_sw128(st + TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; k++) {
+                const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // 32 bytes per K=16 step inside the atom
+                umma_bf16(tmem_base, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(tmem_base, da + koff, dl + koff, idesc, 1u);
+            }
+            umma_commit(&empty[s]);          // frees the stage once the MMAs above have read it
+        }
+        umma_commit(acc_ready);
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait_bounded(acc_ready, 0);
+        tc_fence_after();
+        const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+        const int row = m_tile * TC_BM + quad * 32 + lane;
+        float *out = Gd + (int64_t)row * Np + (int64_t)n_tile * TC_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < 32; u += 4) {
+                float4 f;
+                f.x = __uint_as_float(v[u]);
+                f.y = __uint_as_float(v[u + 1]);
+                f.z = __uint_as_float(v[u + 2]);
+                f.w = __uint_as_float(v[u + 3]);
+                *reinterpret_cast<float4 *>(out + c0 + u) = f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// ---- one-hot operand (static per MSA) ----------------------------------------------------------------
+__global__ void build_xt_kernel(const uint32_t *__restrict__ msa4, __nv_bfloat16 *__restrict__ Xt, int64_t N,
+                                int64_t Nld, int64_t Kp, int L, int q)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (n >= Kp) return;
+    int code = 255;
+    if (n < N) code = (int)((msa4[(int64_t)(j >> 2) * Nld + n] >> (8 * (j & 3))) & 0xffu);
+    for (int b = 0; b < q; b++)
+        Xt[((int64_t)j * q + b) * Kp + n] = __float2bfloat16(code == b ? 1.0f : 0.0f);
+}
+
+// g_J(i<j)[a][b] = scale * (Gd[(j,b),(i,a)] + Gd[(i,a),(j,b)])
+__global__ void finalize_pairs_tc_kernel(const float *__restrict__ Gd, float *__restrict__ gJ, int L, int q,
+                                         int Np, float scale)
+{
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j <= i) return;
+    float *out = gJ + ((int64_t)i * (2 * L - i - 1) / 2 + (j - i - 1)) * q * q;
+    for (int e = threadIdx.x; e < q * q; e += blockDim.x) {
+        const int a = e / q, b = e - a * q;
+        const float v1 = Gd[(int64_t)(j * q + b) * Np + (i * q + a)];
+        const float v2 = Gd[(int64_t)(i * q + a) * Np + (j * q + b)];
+        out[e] = scale * (v1 + v2);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !p)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+static int make_map(CUtensorMap *m, void *base, int64_t rows, int64_t kp, int box_rows)
+{
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+    cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return 1; }
+    return 0;
+}
+
+void plm_tc_geometry(const PlmGeom &g, PlmTcGeom &t)
+{
+    const int64_t lq = (int64_t)g.L * g.q;
+    t.Mp = round_up(lq, TC_BM);
+    t.Np = round_up(lq, TC_BN);
+    t.Kp = round_up(g.N, TC_BK);
+}
+
+int plm_tc_build_xt(const PlmGeom &g, const PlmTcGeom &t, const uint32_t *d_msa4, void *d_xt, cudaStream_t st)
+{
+    EVC_CUDA(cudaMemsetAsync(d_xt, 0, (size_t)t.Mp * t.Kp * 2, st));
+    dim3 grid((unsigned)ceil_div(t.Kp, 256), (unsigned)g.L);
+    build_xt_kernel<<<grid, 256, 0, st>>>(d_msa4, reinterpret_cast<__nv_bfloat16 *>(d_xt), g.N, g.Nld, t.Kp, g.L,
+                                          g.q);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_lo, void *maps_out)
+{
+    CUtensorMap *m = reinterpret_cast<CUtensorMap *>(maps_out);
+    if (make_map(&m[0], d_xt, t.Mp, t.Kp, TC_BM)) return 1;
+    if (make_map(&m[1], d_rt_hi, t.Np, t.Kp, TC_BN)) return 1;
+    if (make_map(&m[2], d_rt_lo, t.Np, t.Kp, TC_BN)) return 1;
+    return 0;
+}
+
+int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, float *d_Gd, cudaStream_t st)
+{
+    const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 128;
+    EVC_CUDA(cudaFuncSetAttribute(plm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(t.Np / TC_BN), (unsigned)(t.Mp / TC_BM));
+    plm_bwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, (int)t.Np, (int)(t.Kp / TC_BK));
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+int plm_tc_finalize_pairs(const PlmGeom &g, const PlmTcGeom &t, const float *d_Gd, float *d_gJ, float scale,
+                          cudaStream_t st)
+{
+    dim3 grid((unsigned)g.L, (unsigned)g.L);
+    finalize_pairs_tc_kernel<<<grid, 128, 0, st>>>(d_Gd, d_gJ, g.L, g.q, (int)t.Np, scale);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+size_t plm_tc_map_bytes() { return 3 * sizeof(CUtensorMap); }
+
+}  // namespace evc

@@ -12,11 +12,16 @@ identically (bit-for-bit, deterministic reductions) on every rank.  The Hamming
 pass shards the upper-triangular pair tiles and all-reduces the int32 counters.
 """
 import ctypes
+import os
 
 import numpy as np
 
 from . import _lib
 from . import lbfgs as _lbfgs
+
+
+# backward implementation of the data term: "gather" (shared-memory bucket kernel) or "tc" (tcgen05 GEMM)
+DEFAULT_BACKWARD = "gather"
 
 
 def _torch():
@@ -83,16 +88,21 @@ class CudaEngine(object):
         return d_counts
 
     # -- (a) PLM ---------------------------------------------------------------------------
-    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6):
-        return CudaPlmProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m)
+    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None):
+        return CudaPlmProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m, backward)
 
 
 class CudaPlmProblem(object):
     """PLM objective on this rank's sequence shard + the L-BFGS vector space
     (see lbfgs.py for the protocol).  All n-vectors are torch CUDA tensors."""
 
-    def __init__(self, engine, codes, weights, q, gap_code, lambda_h, lambda_J, m=6):
+    def __init__(self, engine, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None):
         torch = _torch()
+        if backward is None:
+            backward = os.environ.get("EVC_BACKWARD", DEFAULT_BACKWARD)
+        if backward not in ("gather", "tc"):
+            raise ValueError("backward must be 'gather' or 'tc'")
+        self.backward = backward
         self.engine = engine
         self.lib = engine.lib
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
@@ -113,6 +123,8 @@ class CudaPlmProblem(object):
                                            hi - lo, L, self.q, self.gap_code,
                                            w_shard.ctypes.data_as(ctypes.c_void_p), engine.device_index),
                    "evc_plm_create")
+        if backward == "tc":
+            _lib.check(self.lib.evc_plm_set_backward(self.handle, 1), "evc_plm_set_backward")
         self.n = int(self.lib.evc_plm_num_params(self.handle))
         dev = engine.device
         self.m = m

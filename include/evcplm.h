@@ -84,6 +84,11 @@ int64_t evc_plm_num_params(const evc_plm_t *h);          /* L*q + L(L-1)/2*q*q *
  * No regulariser (so shards can be summed with one all-reduce). */
 int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, void *stream);
 
+/* Backward implementation of the data term: 0 = gather/bucket kernel (shared-memory bound, default),
+ * 1 = dense one-hot contraction on the tcgen05 tensor cores (bf16 hi/lo split of the residuals, fp32
+ * accumulation in TMEM).  Both produce the same gradient within fp32 tolerance; bench.py reports both. */
+int evc_plm_set_backward(evc_plm_t *h, int32_t mode);
+
 /* Per-stage device timing of the LAST evc_plm_eval_data call (CUDA events recorded on the stream the
  * kernels were launched on): ms_out[4] = {expand + clear, forward kernel, backward kernel, finalize}.
  * Used by bench.py to report the dominant kernel's roofline live. */

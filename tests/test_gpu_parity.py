@@ -39,7 +39,7 @@ def gpu_hamming(lib, codes, thr):
     return out
 
 
-def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J):
+def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False):
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     w = np.ascontiguousarray(w, dtype=np.float32)
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -48,6 +48,8 @@ def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J):
     _lib.check(lib.evc_plm_create(ctypes.byref(h), codes.ctypes.data_as(ctypes.c_void_p), N, L, q, gap_code,
                                   w.ctypes.data_as(ctypes.c_void_p), 0), "evc_plm_create")
     try:
+        if tc:
+            _lib.check(lib.evc_plm_set_backward(h, 1), "evc_plm_set_backward")
         assert lib.evc_plm_num_params(h) == x.size
         g = np.zeros_like(x)
         fx = np.zeros(2, dtype=np.float64)
@@ -117,7 +119,7 @@ def test_hamming_full_size_sampled_rows(lib):
 # ------------------------------------------------------------------------------------------------
 # (a) PLM objective + gradient: fp32 device vs float64 oracle
 # ------------------------------------------------------------------------------------------------
-def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1):
+def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=False):
     rng = np.random.default_rng(seed)
     codes = synthetic.synthetic_msa_codes(N, L, seed)
     if gap:
@@ -129,7 +131,7 @@ def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1):
     w = rng.uniform(0.05, 1.0, N).astype(np.float32)
     n = L * q + L * (L - 1) // 2 * q * q
     x = rng.normal(0, xscale, n).astype(np.float32)
-    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J)
+    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J, tc=tc)
     fx64, g64, nll64 = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, lam_h, lam_J, "f64")
     # tolerance: fp32 accumulation over N sequences; measured error of the CPU fp32 port is the yardstick
     fx32, g32, _ = co.plm_eval(codes, w, x, q, lam_h, lam_J, "f32")
@@ -156,6 +158,16 @@ def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1):
 ])
 def test_plm_eval_vs_oracle(lib, N, L, q, gap, seed):
     _check_eval(lib, N, L, q, gap, seed)
+
+
+@pytest.mark.parametrize("N,L,q,gap,seed", [
+    (200, 40, 21, False, 1), (200, 40, 20, True, 1), (1, 2, 21, False, 2), (513, 33, 21, False, 3),
+    (2049, 26, 20, True, 4), (700, 97, 21, False, 5), (3000, 64, 20, True, 6), (300, 30, 5, False, 7),
+])
+def test_plm_eval_tensor_core_backward_vs_oracle(lib, N, L, q, gap, seed):
+    """same tolerance as the gather path: the bf16 hi/lo split of the residuals (16 mantissa bits, fp32
+    accumulation in TMEM) must not be worse than 3x the error of a plain fp32 CPU evaluation."""
+    _check_eval(lib, N, L, q, gap, seed, tc=True)
 
 
 def test_plm_eval_zero_and_large_params(lib):
