@@ -21,7 +21,7 @@ from . import lbfgs as _lbfgs
 
 
 # backward implementation of the data term: "gather" (shared-memory bucket kernel) or "tc" (tcgen05 GEMM)
-DEFAULT_BACKWARD = "gather"
+DEFAULT_BACKWARD = "tc"
 
 
 def _torch():
@@ -142,8 +142,8 @@ class CudaPlmProblem(object):
         self.dotbuf = torch.zeros(1, dtype=torch.float64, device=dev)
         self.last_negloglk = float("nan")
         self.evaluations = 0
-        # kernels per evaluate(): expand, memset G, fwd, bwd, finalize x2, add_reg x2
-        self.launches_per_eval = 8
+        # own kernels per evaluate(): expand, fwd, bwd, finalize pairs + fields, add_reg x2
+        self.launches_per_eval = 7
 
     def close(self):
         if self.handle:
