@@ -563,14 +563,26 @@ __global__ void finalize_fields_kernel(const float *__restrict__ gh_part, const 
                                        float *__restrict__ gh, double *__restrict__ fx, int L, int q, int S,
                                        int ntiles)
 {
-    // one block; fixed summation order => deterministic
+    // blocks 0..L-1: g_h of site i (fixed summation order over tiles => deterministic);
+    // block L: fx = sum of all per-CTA partials (fixed tree)
     __shared__ double s_red[256];
     const int tid = threadIdx.x;
-    for (int e = tid; e < L * q; e += blockDim.x) {
-        const int i = e / q, a = e - i * q;
+    if ((int)blockIdx.x < L) {
+        const int i = blockIdx.x;
+        // 8 partial sums per state, combined in a fixed order
+        const int a = tid & 31, part = tid >> 5;
         float tot = 0.f;
-        for (int t = 0; t < ntiles; t++) tot += gh_part[((int64_t)i * ntiles + t) * S + a];
-        gh[e] = tot;
+        if (a < q)
+            for (int t = part; t < ntiles; t += 8) tot += gh_part[((int64_t)i * ntiles + t) * S + a];
+        __shared__ float s_p[8][32];
+        s_p[part][a] = tot;
+        __syncthreads();
+        if (tid < q) {
+            float v = 0.f;
+            for (int p = 0; p < 8; p++) v += s_p[p][tid];
+            gh[i * q + tid] = v;
+        }
+        return;
     }
     if (fx != nullptr) {
         double acc = 0.0;
@@ -591,7 +603,7 @@ int plm_finalize(const PlmGeom &g, const float *d_G, const float *d_gh_part, con
     dim3 grid((unsigned)g.L, (unsigned)g.L);
     finalize_pairs_kernel<<<grid, 128, 0, st>>>(d_G, d_gJ, g.L, g.Lp, g.q, g.QB, g.S, scale_pair);
     EVC_KERNEL_CHECK();
-    finalize_fields_kernel<<<1, 256, 0, st>>>(d_gh_part, d_fx_part, d_gh, d_fx, g.L, g.q, g.S, g.ntiles_f);
+    finalize_fields_kernel<<<g.L + 1, 256, 0, st>>>(d_gh_part, d_fx_part, d_gh, d_fx, g.L, g.q, g.S, g.ntiles_f);
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -640,7 +652,7 @@ double *reduction_scratch(int nd);   // vecops.cu
 int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                         double *d_fx, cudaStream_t st)
 {
-    finalize_fields_kernel<<<1, 256, 0, st>>>(d_gh_part, d_fx_part, d_gh, d_fx, g.L, g.q, g.S, g.ntiles_f);
+    finalize_fields_kernel<<<g.L + 1, 256, 0, st>>>(d_gh_part, d_fx_part, d_gh, d_fx, g.L, g.q, g.S, g.ntiles_f);
     EVC_KERNEL_CHECK();
     return 0;
 }

@@ -372,14 +372,14 @@ def test_full_size_properties(engine):
     fa, fb = pa.evaluate(pa.x), pb.evaluate(pb.x)
     assert abs((fa + fb) - f_full) <= 1e-9 * abs(f_full) + 1e-3
     gsum = pa.g + pb.g
-    assert float((gsum - g_full).norm() / g_full.norm()) < 2e-6
+    assert float((gsum - g_full).norm() / g_full.norm()) < 1e-5      # fp32 accumulation order differs
     pa.close(); pb.close()
     # (2) linear in the weights
     p2 = engine.plm_problem(codes, 2.0 * w, q, -1, 0.0, 0.0)
     p2.set_x(x)
     f2 = p2.evaluate(p2.x)
     assert abs(f2 - 2 * f_full) <= 1e-7 * abs(f_full)
-    assert float((p2.g - 2 * g_full).norm() / g_full.norm()) < 2e-6
+    assert float((p2.g - 2 * g_full).norm() / g_full.norm()) < 1e-5
     p2.close()
     # (3) gradient is the derivative of fx along a random direction (central difference)
     d = torch.from_numpy(rng.normal(0, 1.0, n).astype(np.float32)).cuda()
@@ -390,7 +390,15 @@ def test_full_size_properties(engine):
     fm = full.evaluate(xs - eps * d)
     dd = float((g_full.double() * d.double()).sum())
     assert abs((fp - fm) / (2 * eps) - dd) <= 2e-3 * abs(dd) + 1e-2
-    # (4) sampled sequences subset against the oracle at full L (N_sub = 1500)
+    # (4) the full-size gradient itself against the float64 oracle (C/OpenMP port, all host cores)
+    fo_full, go_full, _ = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, 0.0, 0.0, "f64")
+    assert abs(f_full - fo_full) <= 2e-6 * abs(fo_full)
+    gfh = g_full.cpu().numpy()
+    rel = np.linalg.norm(gfh - go_full) / np.linalg.norm(go_full)
+    print("full-size gradient vs float64 oracle: rel L2 err %.3e, max abs %.3e (max |g| %.3e)"
+          % (rel, np.abs(gfh - go_full).max(), np.abs(go_full).max()))
+    assert rel <= 1e-5
+    # (5) sampled sequences subset against the oracle at full L (N_sub = 1500)
     full.close()
     sub = engine.plm_problem(codes[:1500], w[:1500], q, -1, 0.0, 0.0)
     sub.set_x(x)
