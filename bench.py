@@ -162,7 +162,7 @@ def run_b200(args):
     t_ham = time.perf_counter() - t0
     weights = (1.0 / counts).astype(np.float32)
 
-    prob = engine.plm_problem(codes, weights, Q, -1, LAMBDA_H, LAMBDA_J, backward=args.backward)
+    prob = engine.plm_problem(codes, weights, Q, -1, LAMBDA_H, LAMBDA_J, backward=args.backward, forward=args.forward)
     prob.set_x(x)
     engine.lib.evc_plm_set_profiling(prob.handle, 1)
     cells = float(n_total) * L * L * Q
@@ -181,8 +181,8 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = engine.kernel_launches
-    stage = np.zeros(4, dtype=np.float32)
-    stage_sum = np.zeros(4, dtype=np.float64)
+    stage = np.zeros(5, dtype=np.float32)
+    stage_sum = np.zeros(5, dtype=np.float64)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -223,9 +223,9 @@ def run_b200(args):
     # forward kernel + 4 B gradient element reduced in the backward kernel, + N*L bytes of MSA.
     peak, peak_src = measured_peak_hbm()
     local_cells = float(n_local) * L * L * Q
-    names = ["expand+clear", "plm_fwd_kernel", "plm_bwd_tc_kernel" if prob.backward == "tc" else "plm_bwd_kernel",
-             "finalize"]
-    dom = 1 if stage_ms[1] >= stage_ms[2] else 2
+    names = ["expand", "tc_gemm_persistent_kernel<fwd logits>" if prob.forward == "tc" else "plm_fwd_kernel",
+             "plm_softmax_kernel", "plm_bwd_tc_kernel" if prob.backward == "tc" else "plm_bwd_kernel", "finalize"]
+    dom = 1 if stage_ms[1] >= stage_ms[3] else 3
     alg_bytes = 4.0 * local_cells + float(n_local) * L
     achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -248,7 +248,7 @@ def run_b200(args):
                    % (world, n) if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (residual buffer %.0f MB, coupling tensors 2x%.0f MB per step)"
                    % (n_local * L * 21 * 4 / 1e6, L * L * 441 * 4 / 1e6),
-                   "lambda_h": LAMBDA_H, "lambda_J": LAMBDA_J, "n_params": n, "backward": prob.backward},
+                   "lambda_h": LAMBDA_H, "lambda_J": LAMBDA_J, "n_params": n, "forward": prob.forward, "backward": prob.backward},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": float(te.item()) * 1e3,
                 "h2d_bytes_per_step": int(4 * n), "d2h_bytes_per_step": int(4 * n + 16)},
@@ -358,6 +358,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--forward", default=None, choices=["gather", "tc"],
+                    help="forward kernel of the data term (default: engine default / EVC_FORWARD)")
     ap.add_argument("--backward", default=None, choices=["gather", "tc"],
                     help="backward kernel of the data term (default: engine default / EVC_BACKWARD)")
     args = ap.parse_args()

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "evc_plm_num_params": (c_i64, [c_void_p]),
     "evc_plm_eval_data": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "evc_plm_set_backward": (ctypes.c_int, [c_void_p, c_i32]),
+    "evc_plm_set_forward": (ctypes.c_int, [c_void_p, c_i32]),
     "evc_plm_set_profiling": (ctypes.c_int, [c_void_p, c_i32]),
     "evc_plm_last_stage_ms": (ctypes.c_int, [c_void_p, c_void_p]),
     "evc_plm_add_regulariser": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32, c_void_p]),

@@ -42,8 +42,18 @@ struct evc_plm {
     void *d_rt_lo = nullptr;
     float *d_Gd = nullptr;
     void *tc_maps = nullptr;        // host: 3 CUtensorMap
+    // tensor-core forward (plm_tc.cu); allocated on first use
+    int fwd_mode = 0;               // 0 = gather kernel, 1 = tcgen05 GEMM + softmax kernel
+    PlmTcfGeom tcf{};
+    void *d_x1h = nullptr;
+    void *d_wt_hi = nullptr;
+    void *d_wt_lo = nullptr;
+    float *d_zt = nullptr;
+    float *d_gh_part2 = nullptr;
+    double *d_fx_part2 = nullptr;
+    void *tcf_maps = nullptr;
     bool profiling = false;         // record CUDA events around the stages of evc_plm_eval_data
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
 };
 
@@ -156,7 +166,14 @@ void evc_plm_destroy(evc_plm_t *h)
     cudaFree(h->d_rt_lo);
     cudaFree(h->d_Gd);
     free(h->tc_maps);
-    for (int k = 0; k < 5; k++)
+    cudaFree(h->d_x1h);
+    cudaFree(h->d_wt_hi);
+    cudaFree(h->d_wt_lo);
+    cudaFree(h->d_zt);
+    cudaFree(h->d_gh_part2);
+    cudaFree(h->d_fx_part2);
+    free(h->tcf_maps);
+    for (int k = 0; k < 6; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     delete h;
 }
@@ -238,27 +255,47 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
     const PlmGeom &g = h->g;
     const bool prof = h->profiling;
     const bool tc = h->bwd_mode == 1;
+    const bool tcf = h->fwd_mode == 1;
+    float *gJ = d_g + (int64_t)g.L * g.q;
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[0], st));
-    if (plm_expand(g, d_x, h->d_W, st)) return 1;
-    if (!tc) EVC_CUDA(cudaMemsetAsync(h->d_G, 0, (size_t)g.w_floats() * sizeof(float), st));
-    if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
-    if (plm_forward(g, h->d_W, d_x, h->d_msa4, h->d_wts, h->d_R, tc ? h->d_rt_hi : nullptr,
-                    tc ? h->d_rt_lo : nullptr, h->tc.Kp, h->d_gh_part, h->d_fx_part, st))
-        return 1;
-    if (prof) EVC_CUDA(cudaEventRecord(h->ev[2], st));
-    if (tc) {
-        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
-        if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
-        if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, d_g + (int64_t)g.L * g.q, 1.0f, st)) return 1;
-        if (plm_finalize_fields(g, h->d_gh_part, h->d_fx_part, d_g, d_fx, st)) return 1;
-    } else {
-        if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
-        if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
-        if (plm_finalize(g, h->d_G, h->d_gh_part, h->d_fx_part, d_g, d_g + (int64_t)g.L * g.q, d_fx, 1.0f, st))
+    if (tcf) {
+        // expand -> tcgen05 logits GEMM -> softmax/residuals -> tcgen05 backward GEMM
+        if (plm_tcf_expand(g, h->tcf, d_x, h->d_wt_hi, h->d_wt_lo, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
+        if (plm_tcf_logits(g, h->tcf, h->tcf_maps, h->d_zt, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[2], st));
+        if (plm_tcf_softmax(g, h->tcf, h->d_zt, d_x, h->d_msa4, h->d_wts, h->d_rt_hi, h->d_rt_lo, h->tc.Kp,
+                            h->d_gh_part2, h->d_fx_part2, st))
             return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
+        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
+        if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, gJ, 1.0f, st)) return 1;
+        if (plm_finalize_fields_n(g, h->d_gh_part2, h->d_fx_part2, d_g, d_fx, h->tcf.ntiles_s, st)) return 1;
+    } else {
+        if (plm_expand(g, d_x, h->d_W, st)) return 1;
+        if (!tc) EVC_CUDA(cudaMemsetAsync(h->d_G, 0, (size_t)g.w_floats() * sizeof(float), st));
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
+        if (plm_forward(g, h->d_W, d_x, h->d_msa4, h->d_wts, h->d_R, tc ? h->d_rt_hi : nullptr,
+                        tc ? h->d_rt_lo : nullptr, h->tc.Kp, h->d_gh_part, h->d_fx_part, st))
+            return 1;
+        if (prof) {
+            EVC_CUDA(cudaEventRecord(h->ev[2], st));
+            EVC_CUDA(cudaEventRecord(h->ev[3], st));
+        }
+        if (tc) {
+            if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+            if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
+            if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, gJ, 1.0f, st)) return 1;
+            if (plm_finalize_fields(g, h->d_gh_part, h->d_fx_part, d_g, d_fx, st)) return 1;
+        } else {
+            if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
+            if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
+            if (plm_finalize(g, h->d_G, h->d_gh_part, h->d_fx_part, d_g, gJ, d_fx, 1.0f, st)) return 1;
+        }
     }
     if (prof) {
-        EVC_CUDA(cudaEventRecord(h->ev[4], st));
+        EVC_CUDA(cudaEventRecord(h->ev[5], st));
         h->ev_valid = true;
     }
     return 0;
@@ -293,12 +330,45 @@ int evc_plm_set_backward(evc_plm_t *h, int32_t mode)
     return 0;
 }
 
+int evc_plm_set_forward(evc_plm_t *h, int32_t mode)
+{
+    if (!h) { set_error("evc_plm_set_forward: null handle"); return 1; }
+    if (mode != 0 && mode != 1) { set_error("evc_plm_set_forward: mode must be 0 (gather) or 1 (tensor core)"); return 1; }
+    EVC_CUDA(cudaSetDevice(h->device));
+    if (mode == 1) {
+        if (evc_plm_set_backward(h, 1)) return 1;     // the tensor-core forward feeds the tensor-core backward
+        if (!h->d_x1h) {
+            plm_tcf_geometry(h->g, h->tcf);
+            const PlmTcfGeom &t = h->tcf;
+            const size_t wb = (size_t)t.Mp * t.Kw * 2, xb = (size_t)t.Ns * t.Kw * 2;
+            const size_t zb = (size_t)t.Mp * t.Ns * sizeof(float);
+            if (cudaMalloc(&h->d_x1h, xb) != cudaSuccess || cudaMalloc(&h->d_wt_hi, wb) != cudaSuccess ||
+                cudaMalloc(&h->d_wt_lo, wb) != cudaSuccess || cudaMalloc(&h->d_zt, zb) != cudaSuccess ||
+                cudaMalloc(&h->d_gh_part2, (size_t)h->g.L * t.ntiles_s * h->g.S * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&h->d_fx_part2, (size_t)h->g.L * t.ntiles_s * sizeof(double)) != cudaSuccess) {
+                set_error(std::string("evc_plm_set_forward: device allocation failed: ") +
+                          cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+            EVC_CUDA(cudaMemset(h->d_wt_hi, 0, wb));
+            EVC_CUDA(cudaMemset(h->d_wt_lo, 0, wb));
+            if (plm_tcf_build_x(h->g, t, h->d_msa4, h->d_x1h, 0)) return 1;
+            EVC_CUDA(cudaDeviceSynchronize());
+            h->tcf_maps = aligned_alloc(64, round_up((int64_t)plm_tc_map_bytes(), 64));
+            if (!h->tcf_maps) { set_error("evc_plm_set_forward: out of host memory"); return 1; }
+            if (plm_tcf_make_maps(t, h->d_wt_hi, h->d_wt_lo, h->d_x1h, h->tcf_maps)) return 1;
+        }
+    }
+    h->fwd_mode = mode;
+    return 0;
+}
+
 int evc_plm_set_profiling(evc_plm_t *h, int32_t enable)
 {
     if (!h) { set_error("evc_plm_set_profiling: null handle"); return 1; }
     EVC_CUDA(cudaSetDevice(h->device));
     if (enable && !h->ev[0])
-        for (int k = 0; k < 5; k++) EVC_CUDA(cudaEventCreate(&h->ev[k]));
+        for (int k = 0; k < 6; k++) EVC_CUDA(cudaEventCreate(&h->ev[k]));
     h->profiling = enable != 0;
     h->ev_valid = false;
     return 0;
@@ -308,8 +378,8 @@ int evc_plm_last_stage_ms(evc_plm_t *h, float *ms_out)
 {
     if (!h || !ms_out) { set_error("evc_plm_last_stage_ms: null pointer"); return 1; }
     if (!h->ev_valid) { set_error("evc_plm_last_stage_ms: no profiled evaluation recorded"); return 1; }
-    EVC_CUDA(cudaEventSynchronize(h->ev[4]));
-    for (int k = 0; k < 4; k++) EVC_CUDA(cudaEventElapsedTime(&ms_out[k], h->ev[k], h->ev[k + 1]));
+    EVC_CUDA(cudaEventSynchronize(h->ev[5]));
+    for (int k = 0; k < 5; k++) EVC_CUDA(cudaEventElapsedTime(&ms_out[k], h->ev[k], h->ev[k + 1]));
     return 0;
 }
 

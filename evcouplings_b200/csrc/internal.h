@@ -67,6 +67,24 @@ int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_l
 int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps_host, float *d_Gd, cudaStream_t st);
 int plm_tc_finalize_pairs(const PlmGeom &g, const PlmTcGeom &t, const float *d_Gd, float *d_gJ, float scale,
                           cudaStream_t st);
+// tensor-core forward: Zt = (Wt_hi + Wt_lo) X^T on tcgen05, then softmax/residual kernel
+struct PlmTcfGeom {
+    int64_t Mp;      // L*q rounded to 128: rows of Wt_hi/Wt_lo and of Zt
+    int64_t Kw;      // L*q rounded to 64: K extent
+    int64_t Ns;      // sequences rounded to 192: rows of the one-hot X, leading dimension of Zt
+    int ntiles_s;    // softmax-kernel sequence tiles (256 sequences)
+};
+void plm_tcf_geometry(const PlmGeom &g, PlmTcfGeom &t);
+int plm_tcf_build_x(const PlmGeom &g, const PlmTcfGeom &t, const uint32_t *d_msa4, void *d_x1h, cudaStream_t st);
+int plm_tcf_make_maps(const PlmTcfGeom &t, void *d_wt_hi, void *d_wt_lo, void *d_x1h, void *maps_out_host);
+int plm_tcf_expand(const PlmGeom &g, const PlmTcfGeom &t, const float *d_x, void *d_wt_hi, void *d_wt_lo,
+                   cudaStream_t st);
+int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps_host, float *d_zt, cudaStream_t st);
+int plm_tcf_softmax(const PlmGeom &g, const PlmTcfGeom &t, const float *d_zt, const float *d_x,
+                    const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
+                    float *d_gh_part, double *d_fx_part, cudaStream_t st);
+int plm_finalize_fields_n(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
+                          double *d_fx, int ntiles, cudaStream_t st);
 int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                         double *d_fx, cudaStream_t st);
 

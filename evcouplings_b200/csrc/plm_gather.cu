@@ -649,6 +649,14 @@ __global__ void add_reg_final_kernel(const double *__restrict__ partial, int nbl
 
 double *reduction_scratch(int nd);   // vecops.cu
 
+int plm_finalize_fields_n(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
+                          double *d_fx, int ntiles, cudaStream_t st)
+{
+    finalize_fields_kernel<<<g.L + 1, 256, 0, st>>>(d_gh_part, d_fx_part, d_gh, d_fx, g.L, g.q, g.S, ntiles);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
 int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                         double *d_fx, cudaStream_t st)
 {

@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -218,6 +220,249 @@ plm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant with a double-buffered TMEM accumulator (2 x 192 columns): the epilogue of tile t
+// overlaps the main loop of tile t+1.  Used for the FORWARD product, which has many short tiles:
+//     Zt[(i,a), n] = sum_(j,b) (Wt_hi + Wt_lo)[(i,a),(j,b)] * X[n,(j,b)]
+// SPLIT_A = 1: operands (A_hi, A_lo, B), two MMAs share B;  SPLIT_A = 0: (A, B_hi, B_lo), two MMAs share A.
+// Tiles are enumerated with the M index fastest so that concurrently running CTAs share the B tile.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int SPLIT_A>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                          const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
+                          int m_tiles, int n_tiles, int num_kb)
+{
+    constexpr int BYTES0 = SPLIT_A ? TC_A_BYTES : TC_A_BYTES;       // operand 0: A or A_hi (128 rows)
+    constexpr int BYTES1 = SPLIT_A ? TC_A_BYTES : TC_B_BYTES;       // operand 1: A_lo or B_hi
+    constexpr int BYTES2 = TC_B_BYTES;                              // operand 2: B or B_lo (192 rows)
+    constexpr int STAGE = BYTES0 + BYTES1 + BYTES2;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                                            ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *acc_full = empty + TC_STAGES;      // [2]
+    uint64_t *acc_empty = acc_full + 2;          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);         // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                mbar_wait_bounded(&empty[s], ph ^ 1u);
+                unsigned char *st = smem + s * STAGE;
+                mbar_expect_tx(&full[s], STAGE);
+                tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
+                tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, SPLIT_A ? m_tile * TC_BM : n_tile * TC_BN, &full[s]);
+                tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+        int it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
+            const int acc = tl & 1;
+            mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((tl >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                mbar_wait_bounded(&full[s], ph);
+                tc_fence_after();
+                unsigned char *st = smem + s * STAGE;
+                const uint64_t d0 = make_desc_sw128(st);
+                const uint64_t d1 = make_desc_sw128(st + BYTES0);
+                const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; k++) {
+                    const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                    const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+                    if (SPLIT_A) {
+                        umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, first);
+                        umma_bf16(tmem_d, d1 + koff, d2 + koff, idesc, 1u);
+                    } else {
+                        umma_bf16(tmem_d, d0 + koff, d1 + koff, idesc, first);
+                        umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&acc_full[acc]);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int quad = warp & 3;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
+            const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
+            const int acc = tl & 1;
+            mbar_wait_bounded(&acc_full[acc], (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
+            float *out = D + row * ldd + (int64_t)n_tile * TC_BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 32; u += 4) {
+                    float4 f;
+                    f.x = __uint_as_float(v[u]);
+                    f.y = __uint_as_float(v[u + 1]);
+                    f.z = __uint_as_float(v[u + 2]);
+                    f.w = __uint_as_float(v[u + 3]);
+                    *reinterpret_cast<float4 *>(out + c0 + u) = f;
+                }
+            }
+            // accumulator drained: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// expand for the tensor-core forward: Wt[(i,a)][(j,b)] = J_ij(a,b) as bf16 hi + lo, both orientations
+__global__ void expand_tc_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ Wt_hi,
+                                 __nv_bfloat16 *__restrict__ Wt_lo, int L, int q, int64_t ldw)
+{
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j <= i) return;
+    const float *J = x + (int64_t)L * q + ((int64_t)i * (2 * L - i - 1) / 2 + (j - i - 1)) * q * q;
+    for (int e = threadIdx.x; e < q * q; e += blockDim.x) {
+        const int a = e / q, b = e - a * q;
+        const float v = J[e];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int64_t p1 = (int64_t)(i * q + a) * ldw + (j * q + b);
+        const int64_t p2 = (int64_t)(j * q + b) * ldw + (i * q + a);
+        Wt_hi[p1] = hi; Wt_lo[p1] = lo;
+        Wt_hi[p2] = hi; Wt_lo[p2] = lo;
+    }
+}
+
+// one-hot operand of the forward product: X[n][(j,b)], K = (j,b) fastest
+__global__ void build_x_kernel(const uint32_t *__restrict__ msa4, __nv_bfloat16 *__restrict__ X, int64_t N,
+                               int64_t Nld, int L, int q, int64_t ldx)
+{
+    const int64_t n = blockIdx.x;
+    if (n >= N) return;
+    for (int e = threadIdx.x; e < L * q; e += blockDim.x) {
+        const int j = e / q, b = e - j * q;
+        const int code = (int)((msa4[(int64_t)(j >> 2) * Nld + n] >> (8 * (j & 3))) & 0xffu);
+        X[n * ldx + e] = __float2bfloat16(code == b ? 1.0f : 0.0f);
+    }
+}
+
+// softmax + residuals from the logits Zt[(i,a)][n] (thread = sequence, fully coalesced)
+template <int Q>
+__global__ void __launch_bounds__(256)
+plm_softmax_kernel(const float *__restrict__ Zt, int64_t ldz, const float *__restrict__ h,
+                   const uint32_t *__restrict__ msa4, const float *__restrict__ wts,
+                   __nv_bfloat16 *__restrict__ Rt_hi, __nv_bfloat16 *__restrict__ Rt_lo, int64_t Kp,
+                   float *__restrict__ gh_part, double *__restrict__ fx_part, PlmGeom g, int ntiles)
+{
+    __shared__ float s_gh[8 * 32];
+    __shared__ double s_fx[8];
+    const int tile = blockIdx.x, i = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t N = g.N;
+    const int64_t n = (int64_t)tile * 256 + tid;
+    const int64_t m = n < N ? n : N - 1;
+    float z[Q];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < Q; a++) {
+        z[a] = Zt[((int64_t)i * Q + a) * ldz + m] + h[i * Q + a];
+        mx = fmaxf(mx, z[a]);
+    }
+    const uint32_t wi = msa4[(int64_t)(i >> 2) * g.Nld + m];
+    const int si = (int)((wi >> (8 * (i & 3))) & 0xffu);
+    const float w = (n < N && si < Q) ? wts[m] : 0.f;
+    float zs = 0.f, sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < Q; a++) {
+        if (a == si) zs = z[a];
+        z[a] = expf(z[a] - mx);
+        sum += z[a];
+    }
+    const double fx_local = (w == 0.f) ? 0.0 : -((double)w * (double)(zs - mx - logf(sum)));
+    const float inv = w / sum;
+#pragma unroll
+    for (int a = 0; a < Q; a++) {
+        z[a] = z[a] * inv - (a == si ? w : 0.f);
+        if (n < N) {
+            const int64_t off = ((int64_t)i * Q + a) * Kp + n;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(z[a]);
+            Rt_hi[off] = hi;
+            Rt_lo[off] = __float2bfloat16_rn(z[a] - __bfloat162float(hi));
+        }
+        const float v = warp_sum(z[a]);
+        if (lane == 0) s_gh[warp * 32 + a] = v;
+    }
+    const double fw = warp_sum(fx_local);
+    if (lane == 0) s_fx[warp] = fw;
+    __syncthreads();
+    if (tid < g.S) {
+        float tot = 0.f;
+        if (tid < Q)
+            for (int ww = 0; ww < 8; ww++) tot += s_gh[ww * 32 + tid];
+        gh_part[((int64_t)i * ntiles + tile) * g.S + tid] = tot;
+    }
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int ww = 0; ww < 8; ww++) tot += s_fx[ww];
+        fx_part[(int64_t)i * ntiles + tile] = tot;
+    }
+}
+
 // ---- one-hot operand (static per MSA) ----------------------------------------------------------------
 __global__ void build_xt_kernel(const uint32_t *__restrict__ msa4, __nv_bfloat16 *__restrict__ Xt, int64_t N,
                                 int64_t Nld, int64_t Kp, int L, int q)
@@ -322,6 +567,87 @@ int plm_tc_finalize_pairs(const PlmGeom &g, const PlmTcGeom &t, const float *d_G
 {
     dim3 grid((unsigned)g.L, (unsigned)g.L);
     finalize_pairs_tc_kernel<<<grid, 128, 0, st>>>(d_Gd, d_gJ, g.L, g.q, (int)t.Np, scale);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+// ---- tensor-core forward -----------------------------------------------------------------------------
+void plm_tcf_geometry(const PlmGeom &g, PlmTcfGeom &t)
+{
+    const int64_t lq = (int64_t)g.L * g.q;
+    t.Mp = round_up(lq, TC_BM);          // rows of Wt / Zt
+    t.Kw = round_up(lq, TC_BK);          // K extent (j,b)
+    t.Ns = round_up(g.N, TC_BN);         // sequences rounded to the 192-column tile
+    t.ntiles_s = (int)ceil_div(g.N, 256);
+}
+
+int plm_tcf_build_x(const PlmGeom &g, const PlmTcfGeom &t, const uint32_t *d_msa4, void *d_x1h, cudaStream_t st)
+{
+    EVC_CUDA(cudaMemsetAsync(d_x1h, 0, (size_t)t.Ns * t.Kw * 2, st));
+    build_x_kernel<<<(unsigned)g.N, 256, 0, st>>>(d_msa4, reinterpret_cast<__nv_bfloat16 *>(d_x1h), g.N, g.Nld, g.L,
+                                                g.q, t.Kw);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+int plm_tcf_make_maps(const PlmTcfGeom &t, void *d_wt_hi, void *d_wt_lo, void *d_x1h, void *maps_out)
+{
+    CUtensorMap *m = reinterpret_cast<CUtensorMap *>(maps_out);
+    if (make_map(&m[0], d_wt_hi, t.Mp, t.Kw, TC_BM)) return 1;
+    if (make_map(&m[1], d_wt_lo, t.Mp, t.Kw, TC_BM)) return 1;
+    if (make_map(&m[2], d_x1h, t.Ns, t.Kw, TC_BN)) return 1;
+    return 0;
+}
+
+int plm_tcf_expand(const PlmGeom &g, const PlmTcfGeom &t, const float *d_x, void *d_wt_hi, void *d_wt_lo,
+                   cudaStream_t st)
+{
+    dim3 grid((unsigned)g.L, (unsigned)g.L);
+    expand_tc_kernel<<<grid, 128, 0, st>>>(d_x, reinterpret_cast<__nv_bfloat16 *>(d_wt_hi),
+                                          reinterpret_cast<__nv_bfloat16 *>(d_wt_lo), g.L, g.q, t.Kw);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+static int sm_count_cached()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, float *d_zt, cudaStream_t st)
+{
+    const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
+    const size_t smem = (size_t)TC_STAGES * (2 * TC_A_BYTES + TC_B_BYTES) + 1024 + 128;
+    EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Ns / TC_BN);
+    const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
+    tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
+                                                                (int)(t.Kw / TC_BK));
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+int plm_tcf_softmax(const PlmGeom &g, const PlmTcfGeom &t, const float *d_zt, const float *d_x,
+                    const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
+                    float *d_gh_part, double *d_fx_part, cudaStream_t st)
+{
+    dim3 grid((unsigned)t.ntiles_s, (unsigned)g.L);
+    __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(d_rt_hi), *lo = reinterpret_cast<__nv_bfloat16 *>(d_rt_lo);
+    switch (g.q) {
+        case 21: plm_softmax_kernel<21><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
+        case 20: plm_softmax_kernel<20><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
+        case 5: plm_softmax_kernel<5><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
+        case 4: plm_softmax_kernel<4><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
+        default: set_error("plm_tcf_softmax: unsupported q"); return 1;
+    }
     EVC_KERNEL_CHECK();
     return 0;
 }

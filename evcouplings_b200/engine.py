@@ -22,6 +22,7 @@ from . import lbfgs as _lbfgs
 
 # backward implementation of the data term: "gather" (shared-memory bucket kernel) or "tc" (tcgen05 GEMM)
 DEFAULT_BACKWARD = "tc"
+DEFAULT_FORWARD = "gather"
 
 
 def _torch():
@@ -88,16 +89,24 @@ class CudaEngine(object):
         return d_counts
 
     # -- (a) PLM ---------------------------------------------------------------------------
-    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None):
-        return CudaPlmProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m, backward)
+    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None, forward=None):
+        return CudaPlmProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m, backward, forward)
 
 
 class CudaPlmProblem(object):
     """PLM objective on this rank's sequence shard + the L-BFGS vector space
     (see lbfgs.py for the protocol).  All n-vectors are torch CUDA tensors."""
 
-    def __init__(self, engine, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None):
+    def __init__(self, engine, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None,
+                 forward=None):
         torch = _torch()
+        if forward is None:
+            forward = os.environ.get("EVC_FORWARD", DEFAULT_FORWARD)
+        if forward not in ("gather", "tc"):
+            raise ValueError("forward must be 'gather' or 'tc'")
+        if forward == "tc":
+            backward = "tc"
+        self.forward = forward
         if backward is None:
             backward = os.environ.get("EVC_BACKWARD", DEFAULT_BACKWARD)
         if backward not in ("gather", "tc"):
@@ -125,6 +134,8 @@ class CudaPlmProblem(object):
                    "evc_plm_create")
         if backward == "tc":
             _lib.check(self.lib.evc_plm_set_backward(self.handle, 1), "evc_plm_set_backward")
+        if forward == "tc":
+            _lib.check(self.lib.evc_plm_set_forward(self.handle, 1), "evc_plm_set_forward")
         self.n = int(self.lib.evc_plm_num_params(self.handle))
         dev = engine.device
         self.m = m
@@ -143,7 +154,7 @@ class CudaPlmProblem(object):
         self.last_negloglk = float("nan")
         self.evaluations = 0
         # own kernels per evaluate(): expand, fwd, bwd, finalize pairs + fields, add_reg x2
-        self.launches_per_eval = 7
+        self.launches_per_eval = 8 if forward == "tc" else 7
 
     def close(self):
         if self.handle:

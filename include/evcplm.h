@@ -88,9 +88,14 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
  * 1 = dense one-hot contraction on the tcgen05 tensor cores (bf16 hi/lo split of the residuals, fp32
  * accumulation in TMEM).  Both produce the same gradient within fp32 tolerance; bench.py reports both. */
 int evc_plm_set_backward(evc_plm_t *h, int32_t mode);
+/* Forward implementation: 0 = gather kernel (fp32 couplings streamed through shared memory),
+ * 1 = logits as a tcgen05 GEMM (couplings split in bf16 hi + lo, fp32 accumulation) followed by a
+ * softmax/residual kernel; mode 1 implies the tensor-core backward. */
+int evc_plm_set_forward(evc_plm_t *h, int32_t mode);
 
 /* Per-stage device timing of the LAST evc_plm_eval_data call (CUDA events recorded on the stream the
- * kernels were launched on): ms_out[4] = {expand + clear, forward kernel, backward kernel, finalize}.
+ * kernels were launched on): ms_out[5] = {expand (+ clear), forward (gather kernel or logits GEMM),
+ * softmax kernel (0 on the gather forward), backward kernel, finalize}.
  * Used by bench.py to report the dominant kernel's roofline live. */
 int evc_plm_set_profiling(evc_plm_t *h, int32_t enable);
 int evc_plm_last_stage_ms(evc_plm_t *h, float *ms_out);

@@ -39,7 +39,7 @@ def gpu_hamming(lib, codes, thr):
     return out
 
 
-def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False):
+def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False, tcf=False):
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     w = np.ascontiguousarray(w, dtype=np.float32)
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -50,6 +50,8 @@ def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False):
     try:
         if tc:
             _lib.check(lib.evc_plm_set_backward(h, 1), "evc_plm_set_backward")
+        if tcf:
+            _lib.check(lib.evc_plm_set_forward(h, 1), "evc_plm_set_forward")
         assert lib.evc_plm_num_params(h) == x.size
         g = np.zeros_like(x)
         fx = np.zeros(2, dtype=np.float64)
@@ -119,7 +121,7 @@ def test_hamming_full_size_sampled_rows(lib):
 # ------------------------------------------------------------------------------------------------
 # (a) PLM objective + gradient: fp32 device vs float64 oracle
 # ------------------------------------------------------------------------------------------------
-def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=False):
+def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=False, tcf=False):
     rng = np.random.default_rng(seed)
     codes = synthetic.synthetic_msa_codes(N, L, seed)
     if gap:
@@ -131,7 +133,7 @@ def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=F
     w = rng.uniform(0.05, 1.0, N).astype(np.float32)
     n = L * q + L * (L - 1) // 2 * q * q
     x = rng.normal(0, xscale, n).astype(np.float32)
-    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J, tc=tc)
+    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J, tc=tc, tcf=tcf)
     fx64, g64, nll64 = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, lam_h, lam_J, "f64")
     # tolerance: fp32 accumulation over N sequences; measured error of the CPU fp32 port is the yardstick
     fx32, g32, _ = co.plm_eval(codes, w, x, q, lam_h, lam_J, "f32")
@@ -142,6 +144,9 @@ def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=F
     assert abs(nll - nll64) <= 2e-6 * abs(nll64)
     assert err_gpu <= max(3.0 * err_c32, 2e-6 * scale), (err_gpu, err_c32, scale)
     assert np.linalg.norm(g - g64) <= 5e-6 * np.linalg.norm(g64)
+    print("eval parity N=%d L=%d q=%d tc=%s tcf=%s: max err %.3e (C fp32 port %.3e), rel L2 %.3e, fx rel %.3e"
+          % (N, L, q, tc, tcf, err_gpu, err_c32, np.linalg.norm(g - g64) / np.linalg.norm(g64),
+             abs(fx - fx64) / abs(fx64)))
     return err_gpu, err_c32
 
 
@@ -168,6 +173,16 @@ def test_plm_eval_tensor_core_backward_vs_oracle(lib, N, L, q, gap, seed):
     """same tolerance as the gather path: the bf16 hi/lo split of the residuals (16 mantissa bits, fp32
     accumulation in TMEM) must not be worse than 3x the error of a plain fp32 CPU evaluation."""
     _check_eval(lib, N, L, q, gap, seed, tc=True)
+
+
+@pytest.mark.parametrize("N,L,q,gap,seed,xscale", [
+    (200, 40, 21, False, 1, 0.1), (200, 40, 20, True, 1, 0.1), (1, 2, 21, False, 2, 0.1),
+    (513, 33, 21, False, 3, 0.1), (2049, 26, 20, True, 4, 0.1), (700, 97, 21, False, 5, 0.1),
+    (3000, 64, 20, True, 6, 0.1), (300, 30, 5, False, 7, 0.1), (400, 24, 21, False, 10, 1.0),
+])
+def test_plm_eval_tensor_core_forward_vs_oracle(lib, N, L, q, gap, seed, xscale):
+    """forward logits on tcgen05 with the couplings split in bf16 hi + lo (16 mantissa bits): same tolerance"""
+    _check_eval(lib, N, L, q, gap, seed, xscale=xscale, tcf=True)
 
 
 def test_plm_eval_zero_and_large_params(lib):
