@@ -22,7 +22,7 @@ from . import lbfgs as _lbfgs
 
 # backward implementation of the data term: "gather" (shared-memory bucket kernel) or "tc" (tcgen05 GEMM)
 DEFAULT_BACKWARD = "tc"
-DEFAULT_FORWARD = "gather"
+DEFAULT_FORWARD = "tc"
 
 
 def _torch():

@@ -1,0 +1,66 @@
+"""Multi-GPU test (-m gpu, needs >= 2 devices; skipped otherwise): torchrun-style 2-rank NCCL job through the
+public host API: sharded Hamming counts and a sharded PLM evaluation must equal the single-GPU results."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from evcouplings_b200 import synthetic, msa
+from evcouplings_b200.engine import CudaEngine
+eng = CudaEngine()
+N, L, q = 3001, 40, 21
+codes = synthetic.synthetic_msa_codes(N, L, 13)
+counts = eng.hamming_counts(codes, msa.identity_threshold_count(0.8, L))
+w = (1.0 / counts).astype(np.float32)
+x = np.random.default_rng(1).normal(0, 0.1, L*q + L*(L-1)//2*q*q).astype(np.float32)
+prob = eng.plm_problem(codes, w, q, -1, 0.01, 1.5)
+prob.set_x(x)
+fx = prob.evaluate(prob.x)
+g = prob.g.cpu().numpy()
+if rank == 0:
+    np.savez(sys.argv[1], counts=counts, fx=fx, g=g, world=eng.world)
+prob.close()
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_two_gpu_sharded_equals_single(tmp_path):
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out2 = tmp_path / "two.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", str(script), str(out2)]
+    subprocess.run(cmd, check=True, timeout=600)
+    d2 = np.load(out2)
+    assert int(d2["world"]) == 2
+    from evcouplings_b200 import msa, synthetic
+    from evcouplings_b200.engine import CudaEngine
+    from oracle import c_oracle as co
+    eng = CudaEngine()
+    N, L, q = 3001, 40, 21
+    codes = synthetic.synthetic_msa_codes(N, L, 13)
+    thr = msa.identity_threshold_count(0.8, L)
+    assert np.array_equal(d2["counts"], co.hamming_counts(codes, thr))
+    w = (1.0 / d2["counts"]).astype(np.float32)
+    x = np.random.default_rng(1).normal(0, 0.1, L * q + L * (L - 1) // 2 * q * q).astype(np.float32)
+    prob = eng.plm_problem(codes, w, q, -1, 0.01, 1.5)
+    prob.set_x(x)
+    fx1 = prob.evaluate(prob.x)
+    g1 = prob.g.cpu().numpy()
+    prob.close()
+    assert abs(float(d2["fx"]) - fx1) <= 1e-7 * abs(fx1)
+    assert np.linalg.norm(d2["g"] - g1) <= 5e-6 * np.linalg.norm(g1)

@@ -142,7 +142,10 @@ def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=F
     scale = np.abs(g64).max()
     assert abs(fx - fx64) <= 2e-6 * abs(fx64), (fx, fx64)
     assert abs(nll - nll64) <= 2e-6 * abs(nll64)
-    assert err_gpu <= max(3.0 * err_c32, 2e-6 * scale), (err_gpu, err_c32, scale)
+    # gather / tensor-core backward: <= 3x the fp32 CPU port.  Tensor-core FORWARD: the couplings enter the
+    # tcgen05 GEMM as bf16 hi + lo (16 mantissa bits, |dJ| <= 2^-17 |J|), stated tolerance 5x / 4e-6 * max|g|
+    fac, rel = (5.0, 4e-6) if tcf else (3.0, 2e-6)
+    assert err_gpu <= max(fac * err_c32, rel * scale), (err_gpu, err_c32, scale)
     assert np.linalg.norm(g - g64) <= 5e-6 * np.linalg.norm(g64)
     print("eval parity N=%d L=%d q=%d tc=%s tcf=%s: max err %.3e (C fp32 port %.3e), rel L2 %.3e, fx rel %.3e"
           % (N, L, q, tc, tcf, err_gpu, err_c32, np.linalg.norm(g - g64) / np.linalg.norm(g64),
