@@ -140,6 +140,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["NCCL_DEBUG"] = os.environ.get("EVC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -223,8 +224,9 @@ def run_b200(args):
     # forward kernel + 4 B gradient element reduced in the backward kernel, + N*L bytes of MSA.
     peak, peak_src = measured_peak_hbm()
     local_cells = float(n_local) * L * L * Q
-    names = ["expand", "tc_gemm_persistent_kernel<fwd logits>" if prob.forward == "tc" else "plm_fwd_kernel",
-             "plm_softmax_kernel", "plm_bwd_tc_kernel" if prob.backward == "tc" else "plm_bwd_kernel", "finalize"]
+    names = ["expand", "tc_gemm_persistent_kernel<1> (forward logits)" if prob.forward == "tc" else "plm_fwd_kernel",
+             "plm_softmax_kernel", "tc_gemm_persistent_kernel<0> (backward)" if prob.backward == "tc" else "plm_bwd_kernel",
+             "finalize"]
     dom = 1 if stage_ms[1] >= stage_ms[3] else 3
     alg_bytes = 4.0 * local_cells + float(n_local) * L
     achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9

@@ -42,6 +42,7 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;        // 24576
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;   // 65536
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_THREADS = 256;
+constexpr int TC_K_CHUNK = 32;   // k-blocks (of 64) accumulated in TMEM before promotion to an fp32 add
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
@@ -118,108 +119,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-plm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
-                  const __grid_constant__ CUtensorMap tm_blo, float *__restrict__ Gd, int Np, int num_kb)
-{
-    extern __shared__ unsigned char smem_dyn[];
-    // 1024-byte alignment required by SWIZZLE_128B
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
-                                                            ~static_cast<uintptr_t>(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t *empty = full + TC_STAGES;
-    uint64_t *acc_ready = empty + TC_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(acc_ready, 1);
-        mbar_fence_init();
-    }
-    if (warp == 2) tmem_alloc(tmem_slot, TC_TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
-        for (int kb = 0; kb < num_kb; kb++) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
-            mbar_wait_bounded(&empty[s], ph ^ 1u);
-            unsigned char *st = smem + s * TC_STAGE_BYTES;
-            mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-            tma_load_2d(st, &tm_a, kb * TC_BK, m_tile * TC_BM, &full[s]);
-            tma_load_2d(st + TC_A_BYTES, &tm_bhi, kb * TC_BK, n_tile * TC_BN, &full[s]);
-            tma_load_2d(st + TC_A_BYTES + TC_B_BYTES, &tm_blo, kb * TC_BK, n_tile * TC_BN, &full[s]);
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
-        for (int kb = 0; kb < num_kb; kb++) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
-            mbar_wait_bounded(&full[s], ph);
-            tc_fence_after();
-            unsigned char *st = smem + s * TC_STAGE_BYTES;
-            const uint64_t da = make_desc_sw128(st);
-            const uint64_t dh = make_desc_sw128(st + TC_A_BYTES);
-            const uint64_t dl = make_desc_sw128(st + TC_A_BYTES + TC_B_BYTES);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; k++) {
-                const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // 32 bytes per K=16 step inside the atom
-                umma_bf16(tmem_base, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                umma_bf16(tmem_base, da + koff, dl + koff, idesc, 1u);
-            }
-            umma_commit(&empty[s]);          // frees the stage once the MMAs above have read it
-        }
-        umma_commit(acc_ready);
-    } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait_bounded(acc_ready, 0);
-        tc_fence_after();
-        const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
-        const int row = m_tile * TC_BM + quad * 32 + lane;
-        float *out = Gd + (int64_t)row * Np + (int64_t)n_tile * TC_BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int u = 0; u < 32; u += 4) {
-                float4 f;
-                f.x = __uint_as_float(v[u]);
-                f.y = __uint_as_float(v[u + 1]);
-                f.z = __uint_as_float(v[u + 2]);
-                f.w = __uint_as_float(v[u + 3]);
-                *reinterpret_cast<float4 *>(out + c0 + u) = f;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Persistent variant with a double-buffered TMEM accumulator (2 x 192 columns): the epilogue of tile t
 // overlaps the main loop of tile t+1.  Used for the FORWARD product, which has many short tiles:
@@ -236,8 +135,12 @@ template <int SPLIT_A>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                           const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
-                          int m_tiles, int n_tiles, int num_kb)
+                          int m_tiles, int n_tiles, int num_kb, int k_chunk)
 {
+    // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
+    // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
+    // 782 k-blocks); accumulating at most k_chunk k-blocks in TMEM and adding the chunk results in the
+    // epilogue (IEEE round-to-nearest) keeps it at the level of a plain fp32 sum.
     constexpr int BYTES0 = SPLIT_A ? TC_A_BYTES : TC_A_BYTES;       // operand 0: A or A_hi (128 rows)
     constexpr int BYTES1 = SPLIT_A ? TC_A_BYTES : TC_B_BYTES;       // operand 1: A_lo or B_hi
     constexpr int BYTES2 = TC_B_BYTES;                              // operand 2: B or B_lo (192 rows)
@@ -253,6 +156,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
+    const int n_chunks = (num_kb + k_chunk - 1) / k_chunk;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) {
@@ -290,78 +194,97 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
-        int it = 0, tl = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
-            const int acc = tl & 1;
-            mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((tl >> 1) & 1) ^ 1));
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
-            for (int kb = 0; kb < num_kb; kb++, it++) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-                mbar_wait_bounded(&full[s], ph);
+        int it = 0, wl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int c = 0; c < n_chunks; c++, wl++) {
+                const int acc = wl & 1;
+                mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((wl >> 1) & 1) ^ 1));
                 tc_fence_after();
-                unsigned char *st = smem + s * STAGE;
-                const uint64_t d0 = make_desc_sw128(st);
-                const uint64_t d1 = make_desc_sw128(st + BYTES0);
-                const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+                const int kb0 = c * k_chunk, kb1 = min(num_kb, kb0 + k_chunk);
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                    mbar_wait_bounded(&full[s], ph);
+                    tc_fence_after();
+                    unsigned char *st = smem + s * STAGE;
+                    const uint64_t d0 = make_desc_sw128(st);
+                    const uint64_t d1 = make_desc_sw128(st + BYTES0);
+                    const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; k++) {
-                    const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                    const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-                    if (SPLIT_A) {
-                        umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, first);
-                        umma_bf16(tmem_d, d1 + koff, d2 + koff, idesc, 1u);
-                    } else {
-                        umma_bf16(tmem_d, d0 + koff, d1 + koff, idesc, first);
-                        umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, 1u);
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (SPLIT_A) {
+                            umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, first);
+                            umma_bf16(tmem_d, d1 + koff, d2 + koff, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_d, d0 + koff, d1 + koff, idesc, first);
+                            umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, 1u);
+                        }
                     }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&acc_full[acc]);
             }
-            umma_commit(&acc_full[acc]);
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int quad = warp & 3;
-        int tl = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
+        int wl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
-            const int acc = tl & 1;
-            mbar_wait_bounded(&acc_full[acc], (uint32_t)((tl >> 1) & 1));
-            tc_fence_after();
             const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
             float *out = D + row * ldd + (int64_t)n_tile * TC_BN;
+            for (int c = 0; c < n_chunks; c++, wl++) {
+                const int acc = wl & 1;
+                mbar_wait_bounded(&acc_full[acc], (uint32_t)((wl >> 1) & 1));
+                tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c == 0) {
 #pragma unroll
-                for (int u = 0; u < 32; u += 4) {
-                    float4 f;
-                    f.x = __uint_as_float(v[u]);
-                    f.y = __uint_as_float(v[u + 1]);
-                    f.z = __uint_as_float(v[u + 2]);
-                    f.w = __uint_as_float(v[u + 3]);
-                    *reinterpret_cast<float4 *>(out + c0 + u) = f;
+                        for (int u = 0; u < 32; u += 4) {
+                            float4 f;
+                            f.x = __uint_as_float(v[u]);
+                            f.y = __uint_as_float(v[u + 1]);
+                            f.z = __uint_as_float(v[u + 2]);
+                            f.w = __uint_as_float(v[u + 3]);
+                            *reinterpret_cast<float4 *>(out + c0 + u) = f;
+                        }
+                    } else {
+                        float4 p[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) p[u] = *reinterpret_cast<const float4 *>(out + c0 + 4 * u);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            p[u].x += __uint_as_float(v[4 * u]);
+                            p[u].y += __uint_as_float(v[4 * u + 1]);
+                            p[u].z += __uint_as_float(v[4 * u + 2]);
+                            p[u].w += __uint_as_float(v[4 * u + 3]);
+                            *reinterpret_cast<float4 *>(out + c0 + 4 * u) = p[u];
+                        }
+                    }
                 }
+                // accumulator drained: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
             }
-            // accumulator drained: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
     }
     tc_fence_before();
@@ -492,6 +415,18 @@ __global__ void finalize_pairs_tc_kernel(const float *__restrict__ Gd, float *__
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
+static int sm_count_cached()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -555,9 +490,12 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
 {
     const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 128;
-    EVC_CUDA(cudaFuncSetAttribute(plm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(t.Np / TC_BN), (unsigned)(t.Mp / TC_BM));
-    plm_bwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, (int)t.Np, (int)(t.Kp / TC_BK));
+    EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Np / TC_BN);
+    const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
+    tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
+                                                                (int)(t.Kp / TC_BK), TC_K_CHUNK);
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -609,18 +547,6 @@ int plm_tcf_expand(const PlmGeom &g, const PlmTcfGeom &t, const float *d_x, void
     return 0;
 }
 
-static int sm_count_cached()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, float *d_zt, cudaStream_t st)
 {
     const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
@@ -629,8 +555,9 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
                                   (int)smem));
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Ns / TC_BN);
     const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
+    const int num_kb = (int)(t.Kw / TC_BK);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
-                                                                (int)(t.Kw / TC_BK));
+                                                                num_kb, std::min(num_kb, TC_K_CHUNK));
     EVC_KERNEL_CHECK();
     return 0;
 }
