@@ -20,8 +20,8 @@
 //                        (A 16 KB + B_hi 24 KB + B_lo 24 KB per stage), mbarrier expect_tx
 //     warp 1 (1 thread)  MMA issuer: 4 x 2 tcgen05.mma.cta_group::1.kind::f16 (M128 N192 K16) per stage,
 //                        tcgen05.commit -> "empty" barrier of the stage; final commit -> accumulator ready
-//     warp 2             TMEM allocator (256 columns)
-//     warps 4..7         epilogue: tcgen05.ld 32x32b.x32 -> registers -> Gd
+//     warp 2             TMEM allocator (512 columns = two 192-column accumulators)
+//     warps 4..11        epilogue: tcgen05.ld 32x32b.x32 -> chunk sums in registers -> global
 // Roofline: tensor pipe.  2 * 2 * Lq^2 * N flop per evaluation (7.1e12 at N=50k, L=200, q=21).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -41,7 +41,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16384
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;        // 24576
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;   // 65536
 constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: epilogue (2 per TMEM lane quadrant)
 constexpr int TC_K_CHUNK = 32;   // k-blocks (of 64) accumulated in TMEM before promotion to an fp32 add
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -165,7 +165,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 4);         // one arrival per epilogue warp
+            mbar_init(&acc_empty[a], 8);         // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -230,20 +230,25 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
-        const int quad = warp & 3;
+        const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+        const int ehalf = (warp - 4) >> 2;      // which half of the tile's columns this warp drains
+        constexpr int ECOLS = TC_BN / 2;        // 96 columns per epilogue warp
         int wl = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
             const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
-            float *out = D + row * ldd + (int64_t)n_tile * TC_BN;
+            float *out = D + row * ldd + (int64_t)n_tile * TC_BN + ehalf * ECOLS;
+            // chunk sums are promoted into registers (IEEE round-to-nearest adds); one store per tile
+            float accr[ECOLS / 32][32];
             for (int c = 0; c < n_chunks; c++, wl++) {
                 const int acc = wl & 1;
                 mbar_wait_bounded(&acc_full[acc], (uint32_t)((wl >> 1) & 1));
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+#pragma unroll
+                for (int cc = 0; cc < ECOLS / 32; cc++) {
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                           (uint32_t)(acc * TC_BN + ehalf * ECOLS + cc * 32);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -256,35 +261,21 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
                         : "r"(taddr)
                         : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c == 0) {
 #pragma unroll
-                        for (int u = 0; u < 32; u += 4) {
-                            float4 f;
-                            f.x = __uint_as_float(v[u]);
-                            f.y = __uint_as_float(v[u + 1]);
-                            f.z = __uint_as_float(v[u + 2]);
-                            f.w = __uint_as_float(v[u + 3]);
-                            *reinterpret_cast<float4 *>(out + c0 + u) = f;
-                        }
-                    } else {
-                        float4 p[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) p[u] = *reinterpret_cast<const float4 *>(out + c0 + 4 * u);
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            p[u].x += __uint_as_float(v[4 * u]);
-                            p[u].y += __uint_as_float(v[4 * u + 1]);
-                            p[u].z += __uint_as_float(v[4 * u + 2]);
-                            p[u].w += __uint_as_float(v[4 * u + 3]);
-                            *reinterpret_cast<float4 *>(out + c0 + 4 * u) = p[u];
-                        }
-                    }
+                    for (int u = 0; u < 32; u++)
+                        accr[cc][u] = (c == 0) ? __uint_as_float(v[u]) : accr[cc][u] + __uint_as_float(v[u]);
                 }
                 // accumulator drained: hand it back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
             }
+#pragma unroll
+            for (int cc = 0; cc < ECOLS / 32; cc++)
+#pragma unroll
+                for (int u = 0; u < 32; u += 4)
+                    *reinterpret_cast<float4 *>(out + cc * 32 + u) =
+                        make_float4(accr[cc][u], accr[cc][u + 1], accr[cc][u + 2], accr[cc][u + 3]);
         }
     }
     tc_fence_before();
@@ -557,7 +548,7 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
     const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
     const int num_kb = (int)(t.Kw / TC_BK);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
-                                                                num_kb, std::min(num_kb, TC_K_CHUNK));
+                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK);
     EVC_KERNEL_CHECK();
     return 0;
 }
