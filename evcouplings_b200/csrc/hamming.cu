@@ -16,7 +16,7 @@
 // Tiling: 128 x 128 pair tiles over the upper triangle (each unordered pair
 // visited once; a tile credits both its rows and its columns), 256 threads,
 // 8x8 pair counters per thread in registers, plane words staged in shared
-// memory 4 words at a time.  The plane buffer (N * 5 * W * 4 bytes; 40 MB at
+// memory 16 words (512 sites) at a time.  The plane buffer (N * 5 * W * 4 bytes; 40 MB at
 // N=200k, L=300) is L2-resident, so the kernel is bound by the integer pipes.
 #include "common.cuh"
 #include "internal.h"
@@ -25,7 +25,7 @@ namespace evc {
 
 constexpr int HP = 5;        // bit planes (codes < 32)
 constexpr int HT = 128;      // pair-tile edge
-constexpr int HWC = 4;       // words staged per step
+constexpr int HWC = 16;      // words staged per step (80 KB of dynamic shared memory => 2 CTAs / SM)
 
 __global__ void hamming_pack_kernel(const uint8_t *__restrict__ codes, int64_t N, int L, int W,
                                     uint32_t *__restrict__ planes)
@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(256, 2)
 hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int thr,
                     int64_t tile_begin, int64_t T, int *__restrict__ counts)
 {
-    __shared__ __align__(16) uint32_t s_row[HWC][HP][HT];
-    __shared__ __align__(16) uint32_t s_col[HWC][HP][HT];
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t (*s_row)[HP][HT] = reinterpret_cast<uint32_t (*)[HP][HT]>(s_dyn);
+    uint32_t (*s_col)[HP][HT] = reinterpret_cast<uint32_t (*)[HP][HT]>(s_dyn + HWC * HP * HT);
     __shared__ int s_rsum[HT];
     __shared__ int s_csum[HT];
 
@@ -185,11 +186,13 @@ int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_iden
         set_error("hamming_count_tiles: tile range out of bounds");
         return 1;
     }
+    const size_t smem = (size_t)2 * HWC * HP * HT * sizeof(uint32_t);
+    EVC_CUDA(cudaFuncSetAttribute(hamming_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int thr = min_identical + (W * 32 - L);   // padded sites always "agree"
     int64_t done = tile_begin;
     while (done < tile_end) {                        // grid.x limit 2^31-1
         const int64_t nblk = (tile_end - done) < (int64_t)1 << 30 ? (tile_end - done) : (int64_t)1 << 30;
-        hamming_tile_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_planes, N, W, thr, done, T, d_counts);
+        hamming_tile_kernel<<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts);
         EVC_KERNEL_CHECK();
         done += nblk;
     }

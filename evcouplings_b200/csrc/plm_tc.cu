@@ -70,6 +70,24 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         : "memory");
 }
 
+// same, with an L2 cache-policy hint (used to keep the operand that every tile re-reads resident in L2)
+__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *tmap, int c0, int c1,
+                                                 uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
@@ -177,6 +195,8 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
+        // SPLIT_A (forward): the coupling matrix (A_hi, A_lo; 71 MB) is re-read by every sequence tile -> evict_last
+        const uint64_t keep = l2_policy_evict_last();
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
@@ -186,8 +206,13 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
                 mbar_wait_bounded(&empty[s], ph ^ 1u);
                 unsigned char *st = smem + s * STAGE;
                 mbar_expect_tx(&full[s], STAGE);
-                tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
-                tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, SPLIT_A ? m_tile * TC_BM : n_tile * TC_BN, &full[s]);
+                if (SPLIT_A) {
+                    tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                    tma_load_2d_hint(st + BYTES0, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                } else {
+                    tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
+                    tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                }
                 tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
             }
         }
@@ -274,8 +299,8 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
             for (int cc = 0; cc < ECOLS / 32; cc++)
 #pragma unroll
                 for (int u = 0; u < 32; u += 4)
-                    *reinterpret_cast<float4 *>(out + cc * 32 + u) =
-                        make_float4(accr[cc][u], accr[cc][u + 1], accr[cc][u + 2], accr[cc][u + 3]);
+                    __stcs(reinterpret_cast<float4 *>(out + cc * 32 + u),      // streaming: do not pollute L2
+                           make_float4(accr[cc][u], accr[cc][u + 1], accr[cc][u + 2], accr[cc][u + 3]));
         }
     }
     tc_fence_before();

@@ -17,4 +17,4 @@ print("total %.2fs" % (time.time() - t0), run.timings)
 print("status", res.optimization_status, "iterations", run.lbfgs.iterations, "evaluations", run.lbfgs.evaluations,
       "ms/iteration %.2f" % (1e3 * run.timings["optimisation_s"] / max(1, run.lbfgs.iterations)),
       "ms/evaluation %.2f" % (1e3 * run.timings["optimisation_s"] / max(1, run.lbfgs.evaluations)))
-print(res.iteration_table.tail(3))
+print(res.iteration_table.head(4)); print(res.iteration_table.tail(3))

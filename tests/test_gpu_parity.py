@@ -188,6 +188,16 @@ def test_plm_eval_tensor_core_forward_vs_oracle(lib, N, L, q, gap, seed, xscale)
     _check_eval(lib, N, L, q, gap, seed, xscale=xscale, tcf=True)
 
 
+@pytest.mark.parametrize("N,L,q,gap,seed", [
+    (3000, 500, 20, True, 41),      # BASELINE configs[3] site count (Pfam-scale L=500), ignore_gaps
+    (1500, 800, 21, False, 42),     # BASELINE configs[4] site count (EVcomplex L=800)
+])
+def test_plm_eval_large_L_shapes(lib, N, L, q, gap, seed):
+    """geometry of the long-alignment configs (more sites than one shared-memory row block / many GEMM tiles)"""
+    _check_eval(lib, N, L, q, gap, seed, tcf=True)
+    _check_eval(lib, N, L, q, gap, seed, tc=False, tcf=False)
+
+
 def test_plm_eval_zero_and_large_params(lib):
     _check_eval(lib, 400, 24, 21, False, 9, xscale=0.0)          # x = 0: uniform softmax
     _check_eval(lib, 400, 24, 21, False, 10, xscale=1.0)         # large couplings: peaked softmax
@@ -425,3 +435,27 @@ def test_full_size_properties(engine):
     assert abs(fs - fo) <= 2e-6 * abs(fo)
     assert np.linalg.norm(sub.g.cpu().numpy() - go) <= 5e-6 * np.linalg.norm(go)
     sub.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# 8(f3): GPU drop-ins of the reference's in-tree numba twins
+# ------------------------------------------------------------------------------------------------
+def test_intree_twin_dropins_vs_reference_outputs(engine, golden_dir):
+    """evcouplings_b200.alignment.{num_cluster_members, frequencies, pair_frequencies} against the outputs of
+    the reference's own functions (alignment.py:1078-1233) stored by tests/golden/make_golden.py"""
+    from evcouplings_b200 import alignment as ga
+    d = np.load(os.path.join(golden_dir, "intree_twins.npz"))
+    for name in ("cfg1", "tie", "odd"):
+        codes = d[name + "_codes"].astype(np.int64)
+        theta = float(d[name + "_theta"])
+        counts = ga.num_cluster_members(codes, theta, engine=engine)
+        assert counts.dtype == np.float64 and np.array_equal(counts, d[name + "_counts"].astype(np.float64))
+        w = 1.0 / counts
+        fi = ga.frequencies(codes, w, 21, engine=engine)
+        assert np.abs(fi - d[name + "_fi"]).max() < 2e-6
+        fij = ga.pair_frequencies(codes, w, 21, fi, engine=engine)
+        L = codes.shape[1]
+        iu, ju = np.triu_indices(L, 1)
+        assert np.abs(fij[iu, ju] - d[name + "_fij_tri"]).max() < 2e-6
+        assert np.abs(fij[ju, iu] - d[name + "_fij_tri"].transpose(0, 2, 1)).max() < 2e-6
+        assert np.allclose(fij[3, 3][np.arange(21), np.arange(21)], fi[3])
