@@ -49,6 +49,15 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_peak_bf16():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -220,25 +229,51 @@ def run_b200(args):
     e2e_value = cells / float(te.item())
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
-    # Algorithmic bytes: 8 B per cell-op per evaluation = 4 B gathered coupling read in the
-    # forward kernel + 4 B gradient element reduced in the backward kernel, + N*L bytes of MSA.
-    peak, peak_src = measured_peak_hbm()
+    # SURVEY 8d figures.  Dense (tensor-core) path: 2*N*(L*q)^2 algorithmic flop per GEMM launch (4*N*(Lq)^2 per
+    # evaluation); each algorithmic product is executed as two bf16 products (hi + lo split of the real-valued
+    # operand, fp32 accumulation) on padded tiles.  Gather path / HBM accounting: 8 B per cell-op per evaluation
+    # = 4 B gathered coupling read (forward) + 4 B gradient element reduced (backward), + N*L bytes of MSA.
+    peak_hbm, peak_src = measured_peak_hbm()
+    peak_tf, peak_tf_src = measured_peak_bf16()
     local_cells = float(n_local) * L * L * Q
+    lq = float(L * Q)
     names = ["expand", "tc_gemm_persistent_kernel<1> (forward logits)" if prob.forward == "tc" else "plm_fwd_kernel",
              "plm_softmax_kernel", "tc_gemm_persistent_kernel<0> (backward)" if prob.backward == "tc" else "plm_bwd_kernel",
              "finalize"]
     dom = 1 if stage_ms[1] >= stage_ms[3] else 3
-    alg_bytes = 4.0 * local_cells + float(n_local) * L
-    achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
-                "whole_eval": {"algorithmic_bytes": 2 * 4.0 * local_cells + n_local * L,
-                               "achieved": (8.0 * local_cells + n_local * L) / (ms_step * 1e-3) / 1e9,
-                               "frac": (8.0 * local_cells + n_local * L) / (ms_step * 1e-3) / 1e9 / peak},
-                "note": "on-chip-bound kernel: achieved > peak means the gathered bytes are served from shared "
-                        "memory/L2, not HBM (see DESIGN.md, profiles/)"}
+    dom_is_tc = (prob.forward == "tc") if dom == 1 else (prob.backward == "tc")
+    hbm_whole = (8.0 * local_cells + n_local * L) / (ms_step * 1e-3) / 1e9
+    # dram bytes per launch from the committed ncu --set full capture (profiles/r1_ncu_full_*.csv), config 2 only
+    ncu_traffic = {("tc", 1): 4.901e9 + 1.243e9, ("tc", 3): 3.225e9 + 0.102e9,
+                   ("gather", 1): 0.081e9 + 0.789e9, ("gather", 3): 1.165e9 + 0.105e9}
+    mode = (prob.forward if dom == 1 else prob.backward)
+    traffic = ncu_traffic.get((mode, dom)) if (world == 1 and n_local == N_PER_GPU) else None
+    if dom_is_tc:
+        alg_flops = 2.0 * n_local * lq * lq
+        pad_m = -(-int(lq) // 128) * 128
+        exec_flops = 2.0 * 2.0 * pad_m * pad_m * (-(-n_local // (192 if dom == 1 else 64)) * (192 if dom == 1 else 64))
+        achieved = alg_flops / (stage_ms[dom] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_tf_src,
+                    "algorithmic_flops_per_launch": alg_flops,
+                    "executed": {"flops_per_launch": exec_flops, "tflops": exec_flops / (stage_ms[dom] * 1e-3) / 1e12,
+                                 "frac_of_peak": exec_flops / (stage_ms[dom] * 1e-3) / 1e12 / peak_tf,
+                                 "note": "each algorithmic product = 2 bf16 products (hi+lo split keeps 16 mantissa "
+                                         "bits of J / of the residuals), tiles padded to 128/192/64"}}
+    else:
+        alg_bytes = 4.0 * local_cells + (float(n_local) * L if dom == 1 else 0.0)
+        achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_hbm, "unit": "GB/s",
+                    "frac": achieved / peak_hbm, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "on-chip-bound kernel: achieved > peak means the gathered bytes are served from shared "
+                            "memory, not HBM (see DESIGN.md, profiles/)"}
+    roofline["stage_ms"] = {k: float(v) for k, v in zip(names, stage_ms)}
+    roofline["hbm_accounting_whole_eval"] = {
+        "algorithmic_bytes": 8.0 * local_cells + n_local * L, "achieved_GBps": hbm_whole, "peak_GBps": peak_hbm,
+        "frac": hbm_whole / peak_hbm,
+        "note": "north-star accounting (8 B per cell-op); >1 because the work is done on-chip (tensor cores / "
+                "shared memory), compulsory HBM traffic is ~6-9 GB per evaluation"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
