@@ -149,7 +149,11 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = os.environ.get("EVC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    if "EVC_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["EVC_NCCL_DEBUG"]
+    else:                                   # keep stdout to the one JSON line (NCCL prints its banner there)
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/null"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
