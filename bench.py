@@ -251,7 +251,7 @@ def run_b200(args):
     ncu_traffic = {("tc", 1): 4.901e9 + 1.243e9, ("tc", 3): 3.225e9 + 0.102e9,
                    ("gather", 1): 0.081e9 + 0.789e9, ("gather", 3): 1.165e9 + 0.105e9}
     mode = (prob.forward if dom == 1 else prob.backward)
-    traffic = ncu_traffic.get((mode, dom)) if (world == 1 and n_local == N_PER_GPU) else None
+    traffic = ncu_traffic.get((mode, dom)) if (world == 1 and n_local == 50000 and L == 200) else None
     if dom_is_tc:
         alg_flops = 2.0 * n_local * lq * lq
         pad_m = -(-int(lq) // 128) * 128
@@ -283,7 +283,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PLM fx+gradient, synthetic MSA N=%d%s L=%d q=%d fp32 (BASELINE configs[1])"
+        "config": {"workload": "PLM fx+gradient, synthetic MSA N=%d%s L=%d q=%d fp32" + (
+                       " (BASELINE configs[1])" if (N_PER_GPU, L) == (50000, 200) else " (non-default shape)")
                    % (N_PER_GPU, " per GPU (sharded, N_total=%d)" % n_total if world > 1 else "", L, Q),
                    "global_sequences": n_total, "parallelism": "dp%d (sequence shards, 1 NCCL all-reduce of %d floats/step)"
                    % (world, n) if world > 1 else "single GPU",
@@ -394,6 +395,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="plm", choices=["plm", "hamming"])
     ap.add_argument("--hamming-n", type=int, default=200000)
+    ap.add_argument("--seqs", type=int, default=None, help="sequences per GPU (default 50000 = BASELINE configs[1])")
+    ap.add_argument("--sites", type=int, default=None, help="alignment length L (default 200)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -404,6 +407,12 @@ def main():
     ap.add_argument("--backward", default=None, choices=["gather", "tc"],
                     help="backward kernel of the data term (default: engine default / EVC_BACKWARD)")
     args = ap.parse_args()
+    global N_PER_GPU, L, LAMBDA_J
+    if args.seqs:
+        N_PER_GPU = args.seqs
+    if args.sites:
+        L = args.sites
+        LAMBDA_J = 0.01 * (Q - 1) * (L - 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "hamming":
         run_hamming(args)
