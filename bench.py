@@ -283,9 +283,9 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PLM fx+gradient, synthetic MSA N=%d%s L=%d q=%d fp32" + (
-                       " (BASELINE configs[1])" if (N_PER_GPU, L) == (50000, 200) else " (non-default shape)")
-                   % (N_PER_GPU, " per GPU (sharded, N_total=%d)" % n_total if world > 1 else "", L, Q),
+        "config": {"workload": ("PLM fx+gradient, synthetic MSA N=%d%s L=%d q=%d fp32"
+                                % (N_PER_GPU, " per GPU (sharded, N_total=%d)" % n_total if world > 1 else "", L, Q))
+                   + (" (BASELINE configs[1])" if (N_PER_GPU, L) == (50000, 200) else " (non-default shape)"),
                    "global_sequences": n_total, "parallelism": "dp%d (sequence shards, 1 NCCL all-reduce of %d floats/step)"
                    % (world, n) if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (residual buffer %.0f MB, coupling tensors 2x%.0f MB per step)"
