@@ -421,6 +421,24 @@ int evc_plm_weighted_counts(evc_plm_t *h, float *d_fi_counts, float *d_fij_count
     return plm_finalize(g, h->d_G, h->d_gh_part, nullptr, d_fi_counts, d_fij_counts, nullptr, 0.5f, st);
 }
 
+// ---- 8(f) rows f1 / f2 ------------------------------------------------------------------------------
+int evc_ec_scores(const float *d_J_tri, const float *d_fij_tri, const float *d_fi, int32_t L, int32_t q,
+                  float *d_fn_raw, float *d_fn_zero_sum, float *d_mi, void *stream)
+{
+    if (!d_J_tri) { set_error("evc_ec_scores: null pointer"); return 1; }
+    return ec_scores(d_J_tri, d_fij_tri, d_fi, L, q, d_fn_raw, d_fn_zero_sum, d_mi, as_stream(stream));
+}
+
+int evc_plm_energies(evc_plm_t *h, const float *d_x, double *d_out, void *stream)
+{
+    if (!h || !d_x || !d_out) { set_error("evc_plm_energies: null pointer"); return 1; }
+    cudaStream_t st = as_stream(stream);
+    const PlmGeom &g = h->g;
+    if (plm_expand(g, d_x, h->d_W, st)) return 1;
+    // the residual buffer (L * Nr * S floats) is free outside an evaluation: reuse it for the per-site partials
+    return plm_energies(g, h->d_W, d_x, h->d_msa4, h->d_R, d_out, st);
+}
+
 // ---- a8 vector algebra --------------------------------------------------------------------------
 int evc_vec_dot(const float *d_a, const float *d_b, int64_t n, double *d_out, void *stream)
 {

@@ -88,6 +88,12 @@ int plm_finalize_fields_n(const PlmGeom &g, const float *d_gh_part, const double
 int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                         double *d_fx, cudaStream_t st);
 
+// model_ops.cu
+int ec_scores(const float *d_J, const float *d_fij, const float *d_fi, int L, int q, float *d_fn_raw,
+              float *d_fn_zs, float *d_mi, cudaStream_t st);
+int plm_energies(const PlmGeom &g, const float *d_W, const float *d_x, const uint32_t *d_msa4, float *d_epart,
+                 double *d_out, cudaStream_t st);
+
 // vecops.cu
 int vec_dot(const float *a, const float *b, int64_t n, double *out, cudaStream_t st);
 int vec_axpby(float *y, const float *x, float a, float b, int64_t n, cudaStream_t st);

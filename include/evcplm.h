@@ -134,6 +134,17 @@ int evc_lbfgs_update_pair(float *d_S_slot, float *d_Y_slot, const float *d_x, co
                           const float *d_g, const float *d_gp, double *d_ys_slot, double *d_yy,
                           int64_t n, void *stream);
 
+/* ---- SURVEY 8(f) "next" rows ------------------------------------------------
+ * f1: per-pair scores of CouplingsModel._calculate_ecs (evcouplings/couplings/model.py:777-827):
+ *     Frobenius norm of each J_ij block in the raw gauge (plmc's _ECs.txt) and in the zero-sum gauge
+ *     (model.py:179-233), and mutual information from f_ij / f_i (d_fij_tri / d_fi / d_mi may be NULL).
+ *     The APC (model.py:744-775) is an L x L host operation.
+ * f2: statistical energies of this handle's sequences under parameters x (model.py:25-60 _hamiltonians):
+ *     d_out[n][3] = {H, H_J, H_h} (double). */
+int evc_ec_scores(const float *d_J_tri, const float *d_fij_tri, const float *d_fi, int32_t L, int32_t q,
+                  float *d_fn_raw, float *d_fn_zero_sum, float *d_mi, void *stream);
+int evc_plm_energies(evc_plm_t *h, const float *d_x, double *d_out, void *stream);
+
 /* ---- a10: EC scores (Frobenius norm of each J block, raw gauge) ---------- */
 int evc_fn_scores(const float *d_J_tri, int32_t L, int32_t q, float *d_fn /* L(L-1)/2 */, void *stream);
 

@@ -134,7 +134,49 @@ def tiny_model():
     print("tiny model fixtures written; iters=%d" % res.nit)
 
 
+def model_consumers():
+    """Reference CouplingsModel outputs (model.py) on the tiny model and on the golden PABP model:
+    ecs table scores, hamiltonians, single-mutant matrix, delta_hamiltonian."""
+    ref_harness.install()
+    from evcouplings.couplings.model import CouplingsModel
+    rng = np.random.default_rng(5)
+    out = {}
+    for name, path in (("tiny", os.path.join(HERE, "tiny.model")),
+                       ("pabp", os.path.join(EX, "PABP_YEAST.model_params"))):
+        cm = CouplingsModel(path)
+        L, q = cm.L, cm.num_symbols
+        iu, ju = np.triu_indices(L, 1)
+        alphabet = "".join(cm.alphabet)
+        tgt = "".join(cm.target_seq)
+        seqs = [tgt] + ["".join(alphabet[k] for k in rng.integers(0, q, L)) for _ in range(40)]
+        # a few sequences close to the target
+        for _ in range(20):
+            s = list(tgt)
+            for p in rng.integers(0, L, 3):
+                s[p] = alphabet[rng.integers(0, q)]
+            seqs.append("".join(s))
+        out[name + "_seqs"] = np.array(seqs)
+        out[name + "_H"] = cm.hamiltonians(seqs)
+        out[name + "_smm"] = cm.single_mut_mat_full
+        out[name + "_fn"] = cm.fn_scores[iu, ju]
+        out[name + "_cn"] = cm.cn_scores[iu, ju]
+        if name == "tiny":
+            out[name + "_mi_raw"] = cm.mi_scores_raw[iu, ju]
+            out[name + "_mi_apc"] = cm.mi_scores_apc[iu, ju]
+        variants = []
+        for _ in range(12):
+            ps = sorted(set(int(p) for p in rng.integers(0, L, 2)))
+            variants.append([(int(cm.index_list[p]), tgt[p], alphabet[rng.integers(0, q)]) for p in ps])
+        out[name + "_var_pos"] = np.array([[v[0][0], v[-1][0]] for v in variants])
+        out[name + "_variants"] = np.array([";".join("%d,%s,%s" % s for s in v) for v in variants])
+        out[name + "_dH"] = np.array([cm.delta_hamiltonian(v) for v in variants])
+    np.savez_compressed(os.path.join(HERE, "model_consumers.npz"), **out)
+    print("model consumer fixtures written; PABP H(target) = %.10f, smm(127,E) = %.10f" % (
+        out["pabp_H"][0, 0], out["pabp_smm"][127 - 123, "ACDEFGHIKLMNPQRSTVWY".index("E"), 0]))
+
+
 if __name__ == "__main__":
     pabp()
     in_tree_twins()
     tiny_model()
+    model_consumers()

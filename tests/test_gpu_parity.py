@@ -507,3 +507,77 @@ def test_pabp_fit_vs_real_plmc_ecs(engine, golden_dir):
              overlap, dJ))
     assert res.fx <= f_golden + 1e-6 * abs(f_golden)      # we are at least as converged as plmc was
     assert rms < 0.03 and corr > 0.995 and overlap >= 0.9
+
+
+# ------------------------------------------------------------------------------------------------
+# 8(f1) EC scoring / 8(f2) energies on the device vs the reference's CouplingsModel outputs
+# ------------------------------------------------------------------------------------------------
+def _golden_models(golden_dir):
+    from evcouplings_b200 import model_ops
+    tiny = model_ops.read_model(os.path.join(golden_dir, "tiny.model"))
+    g = np.load(os.path.join(golden_dir, "pabp_golden.npz"))
+    L, q = 82, 20
+    pabp = dict(L=L, q=q, alphabet=str(g["alphabet"]), target_seq=str(g["target_seq"]), index_list=g["index_list"],
+                fi=g["fi"], h=g["h"], J=g["J"], fij=np.zeros((L * (L - 1) // 2, q, q), dtype=np.float32))
+    return dict(tiny=tiny, pabp=pabp)
+
+
+def test_model_reader_matches_reference_reader(golden_dir):
+    from evcouplings_b200 import model_ops
+    m = model_ops.read_model(os.path.join(golden_dir, "tiny.model"))
+    r = np.load(os.path.join(golden_dir, "tiny_ref_read.npz"))
+    assert np.array_equal(m["J"].astype(np.float64), r["ref_J_tri"]) and np.array_equal(m["h"].astype(np.float64), r["ref_h"])
+    assert np.array_equal(m["fij"].astype(np.float64), r["ref_fij_tri"]) and m["alphabet"] == str(r["ref_alphabet"])
+
+
+def test_ec_table_vs_reference_calculate_ecs(engine, golden_dir):
+    """FN (zero-sum gauge), CN (APC), MI raw/APC of CouplingsModel._calculate_ecs (model.py:777-827)"""
+    from evcouplings_b200 import model_ops
+    ref = np.load(os.path.join(golden_dir, "model_consumers.npz"))
+    models = _golden_models(golden_dir)
+    for name in ("tiny", "pabp"):
+        m = models[name]
+        fn_raw, fn_zs, mi = model_ops.pair_scores(m, engine)
+        assert np.abs(fn_zs - ref[name + "_fn"]).max() < 2e-6
+        tab = model_ops.ec_table(m, engine).sort_values(by=["i", "j"])
+        assert np.abs(tab["cn"].values - ref[name + "_cn"]).max() < 5e-6
+        assert np.abs(fn_raw - np.sqrt((m["J"].astype(np.float64) ** 2).sum(axis=(1, 2)))).max() < 2e-6
+        if name == "tiny":
+            assert np.abs(mi - ref["tiny_mi_raw"]).max() < 2e-6
+            assert np.abs(tab["mi_apc"].values - ref["tiny_mi_apc"]).max() < 5e-6
+    # PABP: the zero-sum CN is the score the reference's CouplingsModel reports (differs from plmc's _ECs.txt)
+    g = np.load(os.path.join(golden_dir, "pabp_golden.npz"))
+    tab = model_ops.ec_table(models["pabp"], engine).sort_values(by=["i", "j"])
+    assert np.abs(tab["cn"].values - g["ref_cn_zero_sum"]).max() < 5e-6
+
+
+def test_hamiltonians_and_mutants_vs_reference(engine, golden_dir):
+    """_hamiltonians / _single_mutant_hamiltonians / _delta_hamiltonian (model.py:25-176) incl. the notebook
+    known answers H(target) = 312.19741128035912 and smm(127, 'E') = -7.6052584765675419"""
+    from evcouplings_b200 import model_ops
+    ref = np.load(os.path.join(golden_dir, "model_consumers.npz"))
+    models = _golden_models(golden_dir)
+    for name in ("tiny", "pabp"):
+        m = models[name]
+        H = model_ops.hamiltonians(m, [str(s) for s in ref[name + "_seqs"]], engine)
+        assert H.shape == ref[name + "_H"].shape
+        assert np.abs(H - ref[name + "_H"]).max() < 2e-4 * max(1.0, np.abs(ref[name + "_H"]).max())
+        smm = model_ops.single_mutant_matrix(m, engine)
+        assert np.abs(smm - ref[name + "_smm"]).max() < 5e-4
+        variants = [[(int(a), b, c) for a, b, c in (s.split(",") for s in str(v).split(";"))]
+                    for v in ref[name + "_variants"]]
+        dH = model_ops.delta_hamiltonians(m, variants, engine)
+        assert np.abs(dH - ref[name + "_dH"]).max() < 5e-4
+    Hp = model_ops.hamiltonians(models["pabp"], [models["pabp"]["target_seq"]], engine)
+    assert abs(Hp[0, 0] - 312.19741128035912) < 2e-4
+    smm = model_ops.single_mutant_matrix(models["pabp"], engine)
+    assert abs(smm[127 - 123, "ACDEFGHIKLMNPQRSTVWY".index("E"), 0] - (-7.6052584765675419)) < 5e-4
+    # throughput case: many sequences at once
+    rng = np.random.default_rng(0)
+    big = rng.integers(0, 20, size=(20000, 82)).astype(np.uint8)
+    Hb = model_ops.hamiltonians(models["pabp"], big, engine)
+    J = po.full_couplings(models["pabp"]["J"].astype(np.float64), 82, 20)
+    k = 777
+    hj = sum(J[i, j, big[k, i], big[k, j]] for i in range(82) for j in range(i + 1, 82))
+    hh = sum(models["pabp"]["h"][i, big[k, i]] for i in range(82))
+    assert abs(Hb[k, 1] - hj) < 2e-4 * max(1.0, abs(hj)) and abs(Hb[k, 2] - hh) < 1e-4
