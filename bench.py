@@ -241,11 +241,12 @@ def run_b200(args):
     peak_tf, peak_tf_src = measured_peak_bf16()
     local_cells = float(n_local) * L * L * Q
     lq = float(L * Q)
-    names = ["expand", "tc_gemm_persistent_kernel<1> (forward logits)" if prob.forward == "tc" else "plm_fwd_kernel",
+    names = ["expand", {"tc": "tc_gemm_persistent_kernel<1> (forward logits)", "tcfused": "tc_fwd_fused_kernel",
+                       "gather": "plm_fwd_kernel"}[prob.forward],
              "plm_softmax_kernel", "tc_gemm_persistent_kernel<0> (backward)" if prob.backward == "tc" else "plm_bwd_kernel",
              "finalize"]
     dom = 1 if stage_ms[1] >= stage_ms[3] else 3
-    dom_is_tc = (prob.forward == "tc") if dom == 1 else (prob.backward == "tc")
+    dom_is_tc = (prob.forward in ("tc", "tcfused")) if dom == 1 else (prob.backward == "tc")
     hbm_whole = (8.0 * local_cells + n_local * L) / (ms_step * 1e-3) / 1e9
     # dram bytes per launch from the committed ncu --set full capture (profiles/r1_ncu_full_*.csv), config 2 only
     ncu_traffic = {("tc", 1): 4.901e9 + 1.243e9, ("tc", 3): 3.225e9 + 0.102e9,
@@ -255,7 +256,10 @@ def run_b200(args):
     if dom_is_tc:
         alg_flops = 2.0 * n_local * lq * lq
         pad_m = -(-int(lq) // 128) * 128
-        exec_flops = 2.0 * 2.0 * pad_m * pad_m * (-(-n_local // (192 if dom == 1 else 64)) * (192 if dom == 1 else 64))
+        pad_n = {"tc": pad_m, "tcfused": -(-L // 8) * 176}.get(prob.forward, pad_m) if dom == 1 else pad_m
+        pad_k = -(-int(lq) // 64) * 64 if dom == 1 else pad_m
+        seq_pad = {"tc": 192, "tcfused": 128}.get(prob.forward, 192) if dom == 1 else 64
+        exec_flops = 2.0 * 2.0 * pad_n * pad_k * (-(-n_local // seq_pad) * seq_pad)
         achieved = alg_flops / (stage_ms[dom] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_tf_src,
@@ -402,7 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--forward", default=None, choices=["gather", "tc"],
+    ap.add_argument("--forward", default=None, choices=["gather", "tc", "tcfused"],
                     help="forward kernel of the data term (default: engine default / EVC_FORWARD)")
     ap.add_argument("--backward", default=None, choices=["gather", "tc"],
                     help="backward kernel of the data term (default: engine default / EVC_BACKWARD)")

@@ -52,6 +52,13 @@ struct evc_plm {
     float *d_gh_part2 = nullptr;
     double *d_fx_part2 = nullptr;
     void *tcf_maps = nullptr;
+    // fused tensor-core forward (softmax epilogue on the accumulator)
+    PlmTcffGeom tcff{};
+    void *d_wp_hi = nullptr;
+    void *d_wp_lo = nullptr;
+    float *d_gh_part3 = nullptr;
+    double *d_fx_part3 = nullptr;
+    void *tcff_maps = nullptr;
     bool profiling = false;         // record CUDA events around the stages of evc_plm_eval_data
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -173,6 +180,11 @@ void evc_plm_destroy(evc_plm_t *h)
     cudaFree(h->d_gh_part2);
     cudaFree(h->d_fx_part2);
     free(h->tcf_maps);
+    cudaFree(h->d_wp_hi);
+    cudaFree(h->d_wp_lo);
+    cudaFree(h->d_gh_part3);
+    cudaFree(h->d_fx_part3);
+    free(h->tcff_maps);
     for (int k = 0; k < 6; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     delete h;
@@ -256,9 +268,25 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
     const bool prof = h->profiling;
     const bool tc = h->bwd_mode == 1;
     const bool tcf = h->fwd_mode == 1;
+    const bool tcff = h->fwd_mode == 2;
     float *gJ = d_g + (int64_t)g.L * g.q;
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[0], st));
-    if (tcf) {
+    if (tcff) {
+        // expand -> fused tcgen05 forward (logits + softmax + residuals) -> tcgen05 backward GEMM
+        if (plm_tcff_expand(g, h->tcff, d_x, h->d_wp_hi, h->d_wp_lo, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
+        if (plm_tcff_forward(g, h->tcff, h->tcff_maps, d_x, h->d_msa4, h->d_wts, h->d_rt_hi, h->d_rt_lo, h->tc.Kp,
+                             h->d_gh_part3, h->d_fx_part3, st))
+            return 1;
+        if (prof) {
+            EVC_CUDA(cudaEventRecord(h->ev[2], st));
+            EVC_CUDA(cudaEventRecord(h->ev[3], st));
+        }
+        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+        if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
+        if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, gJ, 1.0f, st)) return 1;
+        if (plm_finalize_fields_n(g, h->d_gh_part3, h->d_fx_part3, d_g, d_fx, h->tcff.ntile_part, st)) return 1;
+    } else if (tcf) {
         // expand -> tcgen05 logits GEMM -> softmax/residuals -> tcgen05 backward GEMM
         if (plm_tcf_expand(g, h->tcf, d_x, h->d_wt_hi, h->d_wt_lo, st)) return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
@@ -333,31 +361,60 @@ int evc_plm_set_backward(evc_plm_t *h, int32_t mode)
 int evc_plm_set_forward(evc_plm_t *h, int32_t mode)
 {
     if (!h) { set_error("evc_plm_set_forward: null handle"); return 1; }
-    if (mode != 0 && mode != 1) { set_error("evc_plm_set_forward: mode must be 0 (gather) or 1 (tensor core)"); return 1; }
+    if (mode < 0 || mode > 2) {
+        set_error("evc_plm_set_forward: mode must be 0 (gather), 1 (tensor core) or 2 (tensor core, fused softmax)");
+        return 1;
+    }
     EVC_CUDA(cudaSetDevice(h->device));
-    if (mode == 1) {
+    if (mode == 2 && !plm_tcff_supported(h->g)) mode = 1;     // nucleotide alphabets: unfused tensor-core forward
+    if (mode >= 1) {
         if (evc_plm_set_backward(h, 1)) return 1;     // the tensor-core forward feeds the tensor-core backward
         if (!h->d_x1h) {
             plm_tcf_geometry(h->g, h->tcf);
             const PlmTcfGeom &t = h->tcf;
-            const size_t wb = (size_t)t.Mp * t.Kw * 2, xb = (size_t)t.Ns * t.Kw * 2;
-            const size_t zb = (size_t)t.Mp * t.Ns * sizeof(float);
-            if (cudaMalloc(&h->d_x1h, xb) != cudaSuccess || cudaMalloc(&h->d_wt_hi, wb) != cudaSuccess ||
-                cudaMalloc(&h->d_wt_lo, wb) != cudaSuccess || cudaMalloc(&h->d_zt, zb) != cudaSuccess ||
-                cudaMalloc(&h->d_gh_part2, (size_t)h->g.L * t.ntiles_s * h->g.S * sizeof(float)) != cudaSuccess ||
-                cudaMalloc(&h->d_fx_part2, (size_t)h->g.L * t.ntiles_s * sizeof(double)) != cudaSuccess) {
-                set_error(std::string("evc_plm_set_forward: device allocation failed: ") +
-                          cudaGetErrorString(cudaGetLastError()));
+            const size_t xb = (size_t)t.Xrows * t.Kw * 2;
+            if (cudaMalloc(&h->d_x1h, xb) != cudaSuccess) {
+                set_error("evc_plm_set_forward: device allocation failed (one-hot operand)");
                 return 1;
             }
-            EVC_CUDA(cudaMemset(h->d_wt_hi, 0, wb));
-            EVC_CUDA(cudaMemset(h->d_wt_lo, 0, wb));
             if (plm_tcf_build_x(h->g, t, h->d_msa4, h->d_x1h, 0)) return 1;
             EVC_CUDA(cudaDeviceSynchronize());
-            h->tcf_maps = aligned_alloc(64, round_up((int64_t)plm_tc_map_bytes(), 64));
-            if (!h->tcf_maps) { set_error("evc_plm_set_forward: out of host memory"); return 1; }
-            if (plm_tcf_make_maps(t, h->d_wt_hi, h->d_wt_lo, h->d_x1h, h->tcf_maps)) return 1;
         }
+    }
+    if (mode == 1 && !h->d_zt) {
+        const PlmTcfGeom &t = h->tcf;
+        const size_t wb = (size_t)t.Mp * t.Kw * 2;
+        const size_t zb = (size_t)t.Mp * t.Ns * sizeof(float);
+        if (cudaMalloc(&h->d_wt_hi, wb) != cudaSuccess || cudaMalloc(&h->d_wt_lo, wb) != cudaSuccess ||
+            cudaMalloc(&h->d_zt, zb) != cudaSuccess ||
+            cudaMalloc(&h->d_gh_part2, (size_t)h->g.L * t.ntiles_s * h->g.S * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&h->d_fx_part2, (size_t)h->g.L * t.ntiles_s * sizeof(double)) != cudaSuccess) {
+            set_error(std::string("evc_plm_set_forward: device allocation failed: ") +
+                      cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        EVC_CUDA(cudaMemset(h->d_wt_hi, 0, wb));
+        EVC_CUDA(cudaMemset(h->d_wt_lo, 0, wb));
+        h->tcf_maps = aligned_alloc(64, round_up((int64_t)plm_tc_map_bytes(), 64));
+        if (!h->tcf_maps) { set_error("evc_plm_set_forward: out of host memory"); return 1; }
+        if (plm_tcf_make_maps(t, h->d_wt_hi, h->d_wt_lo, h->d_x1h, h->tcf_maps)) return 1;
+    }
+    if (mode == 2 && !h->d_wp_hi) {
+        plm_tcff_geometry(h->g, h->tcff);
+        const PlmTcffGeom &t = h->tcff;
+        const size_t wb = (size_t)t.Np * t.Kw * 2;
+        if (cudaMalloc(&h->d_wp_hi, wb) != cudaSuccess || cudaMalloc(&h->d_wp_lo, wb) != cudaSuccess ||
+            cudaMalloc(&h->d_gh_part3, (size_t)h->g.L * t.ntile_part * h->g.S * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&h->d_fx_part3, (size_t)h->g.L * t.ntile_part * sizeof(double)) != cudaSuccess) {
+            set_error(std::string("evc_plm_set_forward: device allocation failed: ") +
+                      cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        EVC_CUDA(cudaMemset(h->d_wp_hi, 0, wb));
+        EVC_CUDA(cudaMemset(h->d_wp_lo, 0, wb));
+        h->tcff_maps = aligned_alloc(64, round_up((int64_t)plm_tc_map_bytes(), 64));
+        if (!h->tcff_maps) { set_error("evc_plm_set_forward: out of host memory"); return 1; }
+        if (plm_tcff_make_maps(t, h->d_x1h, h->d_wp_hi, h->d_wp_lo, h->tcff_maps)) return 1;
     }
     h->fwd_mode = mode;
     return 0;

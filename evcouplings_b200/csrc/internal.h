@@ -71,7 +71,8 @@ int plm_tc_finalize_pairs(const PlmGeom &g, const PlmTcGeom &t, const float *d_G
 struct PlmTcfGeom {
     int64_t Mp;      // L*q rounded to 128: rows of Wt_hi/Wt_lo and of Zt
     int64_t Kw;      // L*q rounded to 64: K extent
-    int64_t Ns;      // sequences rounded to 192: rows of the one-hot X, leading dimension of Zt
+    int64_t Ns;      // sequences rounded to 192: leading dimension of Zt
+    int64_t Xrows;   // allocated rows of the one-hot X (N rounded to 384)
     int ntiles_s;    // softmax-kernel sequence tiles (256 sequences)
 };
 void plm_tcf_geometry(const PlmGeom &g, PlmTcfGeom &t);
@@ -83,6 +84,23 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps_host,
 int plm_tcf_softmax(const PlmGeom &g, const PlmTcfGeom &t, const float *d_zt, const float *d_x,
                     const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
                     float *d_gh_part, double *d_fx_part, cudaStream_t st);
+// fused tensor-core forward (softmax / residual epilogue on the TMEM accumulator)
+struct PlmTcffGeom {
+    int n_tiles;       // site tiles (8 sites = 176 padded columns each)
+    int m_tiles;       // sequence tiles (128 sequences)
+    int64_t Np;        // rows of the padded coupling operand Wp_hi / Wp_lo
+    int64_t Kw;        // K extent (L*q rounded to 64)
+    int64_t Xrows;     // allocated rows of X
+    int ntile_part;    // partial-sum slots per site (m_tiles * 4)
+};
+void plm_tcff_geometry(const PlmGeom &g, PlmTcffGeom &t);
+bool plm_tcff_supported(const PlmGeom &g);
+int plm_tcff_make_maps(const PlmTcffGeom &t, void *d_x1h, void *d_wp_hi, void *d_wp_lo, void *maps_out_host);
+int plm_tcff_expand(const PlmGeom &g, const PlmTcffGeom &t, const float *d_x, void *d_wp_hi, void *d_wp_lo,
+                    cudaStream_t st);
+int plm_tcff_forward(const PlmGeom &g, const PlmTcffGeom &t, const void *maps_host, const float *d_x,
+                     const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
+                     float *d_gh_part, double *d_fx_part, cudaStream_t st);
 int plm_finalize_fields_n(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                           double *d_fx, int ntiles, cudaStream_t st);
 int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,

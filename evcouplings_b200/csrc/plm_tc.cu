@@ -308,6 +308,233 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused forward: logits GEMM with the softmax / residual epilogue on the accumulator.
+//   D[n, (i,a)] = sum_(j,b) X[n,(j,b)] * (Wp_hi + Wp_lo)[(i,a),(j,b)]        sequences on M (one TMEM lane each)
+// An N tile is 8 sites = 168 columns + 8 zero columns (UMMA N = 176); each of the 8 epilogue warps owns 32
+// sequences x 4 sites, so a thread sees whole 21-state logit vectors of its sequence: +h, softmax, fx,
+// residuals, bf16 hi/lo split written transposed (sequence fastest) straight into the operand of the backward
+// GEMM.  The 847 MB logits matrix never exists.  Per-(site, 32-sequence group) partials of g_h / fx keep the
+// reduction deterministic.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TF_BN = 176;                         // 8 sites x 21 states + 8 pad
+constexpr int TF_SITES = 8;
+constexpr int TF_B_BYTES = TF_BN * TC_BK * 2;      // 22528
+constexpr int TF_STAGE = TC_A_BYTES + 2 * TF_B_BYTES;   // 61440
+
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *v);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t *v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t *v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
+                    const __grid_constant__ CUtensorMap tm_wlo, const float *__restrict__ h,
+                    const uint32_t *__restrict__ msa4, const float *__restrict__ wts,
+                    __nv_bfloat16 *__restrict__ Rt_hi, __nv_bfloat16 *__restrict__ Rt_lo, int64_t Kp,
+                    float *__restrict__ gh_part, double *__restrict__ fx_part, PlmGeom g, int m_tiles, int n_tiles,
+                    int num_kb)
+{
+    constexpr int Q = 21;                          // states per site of this instantiation (q = 21 or 20 -> S = 21)
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                                            ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TF_STAGE);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *acc_full = empty + TC_STAGES;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+    const int q = g.q;                             // 21, or 20 with the ignored gap (column 20 of a site is then zero)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 8);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: tiles enumerated with the site tile fastest => concurrent CTAs share X tiles =====
+        const uint64_t keep = l2_policy_evict_last();
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                mbar_wait_bounded(&empty[s], ph ^ 1u);
+                unsigned char *st = smem + s * TF_STAGE;
+                mbar_expect_tx(&full[s], TF_STAGE);
+                tma_load_2d(st, &tm_x, kb * TC_BK, m_tile * TC_BM, &full[s]);
+                tma_load_2d_hint(st + TC_A_BYTES, &tm_whi, kb * TC_BK, n_tile * TF_BN, &full[s], keep);
+                tma_load_2d_hint(st + TC_A_BYTES + TF_B_BYTES, &tm_wlo, kb * TC_BK, n_tile * TF_BN, &full[s], keep);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TF_BN);
+        int it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
+            const int acc = tl & 1;
+            mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((tl >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TF_BN);
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+                mbar_wait_bounded(&full[s], ph);
+                tc_fence_after();
+                unsigned char *st = smem + s * TF_STAGE;
+                const uint64_t da = make_desc_sw128(st);
+                const uint64_t dh = make_desc_sw128(st + TC_A_BYTES);
+                const uint64_t dl = make_desc_sw128(st + TC_A_BYTES + TF_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; k++) {
+                    const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                    umma_bf16(tmem_d, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_d, da + koff, dl + koff, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&acc_full[acc]);
+        }
+    } else if (warp >= 4) {
+        // ===== fused epilogue: thread = sequence, 4 sites =====
+        const int quad = warp & 3;
+        const int ehalf = (warp - 4) >> 2;
+        const int ntile_part = m_tiles * 4;           // partial slots per site: (sequence tile, quadrant)
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
+            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            const int acc = tl & 1;
+            const int64_t n = (int64_t)m_tile * TC_BM + quad * 32 + lane;
+            const int64_t nc = n < g.N ? n : g.N - 1;
+            const float wn = n < g.N ? wts[nc] : 0.f;
+            mbar_wait_bounded(&acc_full[acc], (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            uint32_t v[84];
+            const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TF_BN + ehalf * 88);
+            tmem_ld_cols<32>(t0, v);
+            tmem_ld_cols<32>(t0 + 32, v + 32);
+            tmem_ld_cols<16>(t0 + 64, v + 64);
+            tmem_ld_cols<4>(t0 + 80, v + 80);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // logits are in registers: the accumulator can be reused by the MMA issuer right away
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int i = n_tile * TF_SITES + ehalf * 4 + s;
+                if (i >= g.L) break;                                   // padding sites of the last tile (uniform)
+                const int si = (int)((msa4[(int64_t)(i >> 2) * g.Nld + nc] >> (8 * (i & 3))) & 0xffu);
+                const float w = si < q ? wn : 0.f;
+                float z[Q];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int a = 0; a < Q; a++) {
+                    z[a] = (a < q) ? __uint_as_float(v[s * Q + a]) + h[i * q + a] : -INFINITY;
+                    mx = fmaxf(mx, z[a]);
+                }
+                float zs = 0.f, sum = 0.f;
+#pragma unroll
+                for (int a = 0; a < Q; a++) {
+                    if (a == si) zs = z[a];
+                    z[a] = (a < q) ? expf(z[a] - mx) : 0.f;
+                    sum += z[a];
+                }
+                const double fx_local = (w == 0.f) ? 0.0 : -((double)w * (double)(zs - mx - logf(sum)));
+                const float inv = w / sum;
+                float *ghp = gh_part + ((int64_t)i * ntile_part + m_tile * 4 + quad) * g.S;
+#pragma unroll
+                for (int a = 0; a < Q; a++) {
+                    const float r = z[a] * inv - (a == si ? w : 0.f);
+                    if (a < q) {
+                        if (n < g.N) {
+                            const int64_t off = ((int64_t)i * q + a) * Kp + n;
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(r);
+                            Rt_hi[off] = hi;
+                            Rt_lo[off] = __float2bfloat16_rn(r - __bfloat162float(hi));
+                        }
+                    }
+                    const float tot = warp_sum(r);
+                    if (lane == 0) ghp[a] = (a < q) ? tot : 0.f;
+                }
+                const double fw = warp_sum(fx_local);
+                if (lane == 0) fx_part[(int64_t)i * ntile_part + m_tile * 4 + quad] = fw;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// expand for the fused forward: rows regrouped as [site tile][8 sites x q states (+ zero pad to 176)]
+__global__ void expand_tcf_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ Wp_hi,
+                                  __nv_bfloat16 *__restrict__ Wp_lo, int L, int q, int64_t ldw)
+{
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j <= i) return;
+    const float *J = x + (int64_t)L * q + ((int64_t)i * (2 * L - i - 1) / 2 + (j - i - 1)) * q * q;
+    const int64_t ri = (int64_t)(i / TF_SITES) * TF_BN + (i % TF_SITES) * 21;     // padded row base of site i
+    const int64_t rj = (int64_t)(j / TF_SITES) * TF_BN + (j % TF_SITES) * 21;
+    for (int e = threadIdx.x; e < q * q; e += blockDim.x) {
+        const int a = e / q, b = e - a * q;
+        const float v = J[e];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int64_t p1 = (ri + a) * ldw + (j * q + b);        // row (i,a), K index (j,b)
+        const int64_t p2 = (rj + b) * ldw + (i * q + a);        // row (j,b), K index (i,a)
+        Wp_hi[p1] = hi; Wp_lo[p1] = lo;
+        Wp_hi[p2] = hi; Wp_lo[p2] = lo;
+    }
+}
+
 // expand for the tensor-core forward: Wt[(i,a)][(j,b)] = J_ij(a,b) as bf16 hi + lo, both orientations
 __global__ void expand_tc_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ Wt_hi,
                                  __nv_bfloat16 *__restrict__ Wt_lo, int L, int q, int64_t ldw)
@@ -532,12 +759,13 @@ void plm_tcf_geometry(const PlmGeom &g, PlmTcfGeom &t)
     t.Mp = round_up(lq, TC_BM);          // rows of Wt / Zt
     t.Kw = round_up(lq, TC_BK);          // K extent (j,b)
     t.Ns = round_up(g.N, TC_BN);         // sequences rounded to the 192-column tile
+    t.Xrows = round_up(g.N, 384);        // allocation of X: covers 128- and 192-row tilings
     t.ntiles_s = (int)ceil_div(g.N, 256);
 }
 
 int plm_tcf_build_x(const PlmGeom &g, const PlmTcfGeom &t, const uint32_t *d_msa4, void *d_x1h, cudaStream_t st)
 {
-    EVC_CUDA(cudaMemsetAsync(d_x1h, 0, (size_t)t.Ns * t.Kw * 2, st));
+    EVC_CUDA(cudaMemsetAsync(d_x1h, 0, (size_t)t.Xrows * t.Kw * 2, st));
     build_x_kernel<<<(unsigned)g.N, 256, 0, st>>>(d_msa4, reinterpret_cast<__nv_bfloat16 *>(d_x1h), g.N, g.Nld, g.L,
                                                 g.q, t.Kw);
     EVC_KERNEL_CHECK();
@@ -549,7 +777,7 @@ int plm_tcf_make_maps(const PlmTcfGeom &t, void *d_wt_hi, void *d_wt_lo, void *d
     CUtensorMap *m = reinterpret_cast<CUtensorMap *>(maps_out);
     if (make_map(&m[0], d_wt_hi, t.Mp, t.Kw, TC_BM)) return 1;
     if (make_map(&m[1], d_wt_lo, t.Mp, t.Kw, TC_BM)) return 1;
-    if (make_map(&m[2], d_x1h, t.Ns, t.Kw, TC_BN)) return 1;
+    if (make_map(&m[2], d_x1h, t.Xrows, t.Kw, TC_BN)) return 1;
     return 0;
 }
 
@@ -591,6 +819,54 @@ int plm_tcf_softmax(const PlmGeom &g, const PlmTcfGeom &t, const float *d_zt, co
         case 4: plm_softmax_kernel<4><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
         default: set_error("plm_tcf_softmax: unsupported q"); return 1;
     }
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+// ---- fused tensor-core forward ------------------------------------------------------------------------
+void plm_tcff_geometry(const PlmGeom &g, PlmTcffGeom &t)
+{
+    t.n_tiles = (int)ceil_div(g.L, TF_SITES);
+    t.Np = (int64_t)t.n_tiles * TF_BN;
+    t.Kw = round_up((int64_t)g.L * g.q, TC_BK);
+    t.m_tiles = (int)ceil_div(g.N, TC_BM);
+    t.Xrows = round_up(g.N, 384);                  // covers both the 128-row and the 192-row tilings of X
+    t.ntile_part = t.m_tiles * 4;
+}
+
+bool plm_tcff_supported(const PlmGeom &g) { return g.S == 21; }
+
+int plm_tcff_make_maps(const PlmTcffGeom &t, void *d_x1h, void *d_wp_hi, void *d_wp_lo, void *maps_out)
+{
+    CUtensorMap *m = reinterpret_cast<CUtensorMap *>(maps_out);
+    if (make_map(&m[0], d_x1h, t.Xrows, t.Kw, TC_BM)) return 1;
+    if (make_map(&m[1], d_wp_hi, t.Np, t.Kw, TF_BN)) return 1;
+    if (make_map(&m[2], d_wp_lo, t.Np, t.Kw, TF_BN)) return 1;
+    return 0;
+}
+
+int plm_tcff_expand(const PlmGeom &g, const PlmTcffGeom &t, const float *d_x, void *d_wp_hi, void *d_wp_lo,
+                    cudaStream_t st)
+{
+    dim3 grid((unsigned)g.L, (unsigned)g.L);
+    expand_tcf_kernel<<<grid, 128, 0, st>>>(d_x, reinterpret_cast<__nv_bfloat16 *>(d_wp_hi),
+                                           reinterpret_cast<__nv_bfloat16 *>(d_wp_lo), g.L, g.q, t.Kw);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+int plm_tcff_forward(const PlmGeom &g, const PlmTcffGeom &t, const void *maps, const float *d_x,
+                     const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
+                     float *d_gh_part, double *d_fx_part, cudaStream_t st)
+{
+    const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
+    const size_t smem = (size_t)TC_STAGES * TF_STAGE + 1024 + 128;
+    EVC_CUDA(cudaFuncSetAttribute(tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(sm_count_cached(), t.m_tiles * t.n_tiles);
+    tc_fwd_fused_kernel<<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_x, d_msa4, d_wts,
+                                                        reinterpret_cast<__nv_bfloat16 *>(d_rt_hi),
+                                                        reinterpret_cast<__nv_bfloat16 *>(d_rt_lo), Kp, d_gh_part,
+                                                        d_fx_part, g, t.m_tiles, t.n_tiles, (int)(t.Kw / TC_BK));
     EVC_KERNEL_CHECK();
     return 0;
 }

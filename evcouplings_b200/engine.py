@@ -102,9 +102,9 @@ class CudaPlmProblem(object):
         torch = _torch()
         if forward is None:
             forward = os.environ.get("EVC_FORWARD", DEFAULT_FORWARD)
-        if forward not in ("gather", "tc"):
-            raise ValueError("forward must be 'gather' or 'tc'")
-        if forward == "tc":
+        if forward not in ("gather", "tc", "tcfused"):
+            raise ValueError("forward must be 'gather', 'tc' or 'tcfused'")
+        if forward in ("tc", "tcfused"):
             backward = "tc"
         self.forward = forward
         if backward is None:
@@ -134,8 +134,9 @@ class CudaPlmProblem(object):
                    "evc_plm_create")
         if backward == "tc":
             _lib.check(self.lib.evc_plm_set_backward(self.handle, 1), "evc_plm_set_backward")
-        if forward == "tc":
-            _lib.check(self.lib.evc_plm_set_forward(self.handle, 1), "evc_plm_set_forward")
+        if forward in ("tc", "tcfused"):
+            _lib.check(self.lib.evc_plm_set_forward(self.handle, 2 if forward == "tcfused" else 1),
+                       "evc_plm_set_forward")
         self.n = int(self.lib.evc_plm_num_params(self.handle))
         dev = engine.device
         self.m = m
@@ -154,7 +155,7 @@ class CudaPlmProblem(object):
         self.last_negloglk = float("nan")
         self.evaluations = 0
         # own kernels per evaluate(): expand, fwd, bwd, finalize pairs + fields, add_reg x2
-        self.launches_per_eval = 8 if forward == "tc" else 7
+        self.launches_per_eval = {"tc": 8, "tcfused": 7, "gather": 7}[forward]
 
     def close(self):
         if self.handle:

@@ -90,7 +90,8 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
 int evc_plm_set_backward(evc_plm_t *h, int32_t mode);
 /* Forward implementation: 0 = gather kernel (fp32 couplings streamed through shared memory),
  * 1 = logits as a tcgen05 GEMM (couplings split in bf16 hi + lo, fp32 accumulation) followed by a
- * softmax/residual kernel; mode 1 implies the tensor-core backward. */
+ * softmax/residual kernel; 2 = the same GEMM with softmax / residuals fused into its epilogue (no logits
+ * matrix in HBM; protein alphabets, falls back to 1 otherwise).  Modes 1 and 2 imply the tensor-core backward. */
 int evc_plm_set_forward(evc_plm_t *h, int32_t mode);
 
 /* Per-stage device timing of the LAST evc_plm_eval_data call (CUDA events recorded on the stream the

@@ -39,7 +39,7 @@ def gpu_hamming(lib, codes, thr):
     return out
 
 
-def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False, tcf=False):
+def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False, tcf=False, fused=False):
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     w = np.ascontiguousarray(w, dtype=np.float32)
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -51,7 +51,7 @@ def gpu_eval_host(lib, codes, w, x, q, gap_code, lam_h, lam_J, tc=False, tcf=Fal
         if tc:
             _lib.check(lib.evc_plm_set_backward(h, 1), "evc_plm_set_backward")
         if tcf:
-            _lib.check(lib.evc_plm_set_forward(h, 1), "evc_plm_set_forward")
+            _lib.check(lib.evc_plm_set_forward(h, 2 if fused else 1), "evc_plm_set_forward")
         assert lib.evc_plm_num_params(h) == x.size
         g = np.zeros_like(x)
         fx = np.zeros(2, dtype=np.float64)
@@ -121,7 +121,7 @@ def test_hamming_full_size_sampled_rows(lib):
 # ------------------------------------------------------------------------------------------------
 # (a) PLM objective + gradient: fp32 device vs float64 oracle
 # ------------------------------------------------------------------------------------------------
-def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=False, tcf=False):
+def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=False, tcf=False, fused=False):
     rng = np.random.default_rng(seed)
     codes = synthetic.synthetic_msa_codes(N, L, seed)
     if gap:
@@ -133,7 +133,7 @@ def _check_eval(lib, N, L, q, gap, seed, lam_h=0.01, lam_J=2.0, xscale=0.1, tc=F
     w = rng.uniform(0.05, 1.0, N).astype(np.float32)
     n = L * q + L * (L - 1) // 2 * q * q
     x = rng.normal(0, xscale, n).astype(np.float32)
-    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J, tc=tc, tcf=tcf)
+    fx, g, nll = gpu_eval_host(lib, codes, w, x, q, q if gap else -1, lam_h, lam_J, tc=tc, tcf=tcf, fused=fused)
     fx64, g64, nll64 = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, lam_h, lam_J, "f64")
     # tolerance: fp32 accumulation over N sequences; measured error of the CPU fp32 port is the yardstick
     fx32, g32, _ = co.plm_eval(codes, w, x, q, lam_h, lam_J, "f32")
@@ -184,8 +184,10 @@ def test_plm_eval_tensor_core_backward_vs_oracle(lib, N, L, q, gap, seed):
     (3000, 64, 20, True, 6, 0.1), (300, 30, 5, False, 7, 0.1), (400, 24, 21, False, 10, 1.0),
 ])
 def test_plm_eval_tensor_core_forward_vs_oracle(lib, N, L, q, gap, seed, xscale):
-    """forward logits on tcgen05 with the couplings split in bf16 hi + lo (16 mantissa bits): same tolerance"""
+    """forward logits on tcgen05 with the couplings split in bf16 hi + lo (16 mantissa bits): same tolerance;
+    both the unfused (logits matrix + softmax kernel) and the fused-epilogue variants"""
     _check_eval(lib, N, L, q, gap, seed, xscale=xscale, tcf=True)
+    _check_eval(lib, N, L, q, gap, seed, xscale=xscale, tcf=True, fused=True)
 
 
 @pytest.mark.parametrize("N,L,q,gap,seed", [
@@ -195,6 +197,7 @@ def test_plm_eval_tensor_core_forward_vs_oracle(lib, N, L, q, gap, seed, xscale)
 def test_plm_eval_large_L_shapes(lib, N, L, q, gap, seed):
     """geometry of the long-alignment configs (more sites than one shared-memory row block / many GEMM tiles)"""
     _check_eval(lib, N, L, q, gap, seed, tcf=True)
+    _check_eval(lib, N, L, q, gap, seed, tcf=True, fused=True)
     _check_eval(lib, N, L, q, gap, seed, tc=False, tcf=False)
 
 
