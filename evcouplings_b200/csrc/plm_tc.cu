@@ -311,7 +311,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
 // ---------------------------------------------------------------------------------------------------
 // Fused forward: logits GEMM with the softmax / residual epilogue on the accumulator.
 //   D[n, (i,a)] = sum_(j,b) X[n,(j,b)] * (Wp_hi + Wp_lo)[(i,a),(j,b)]        sequences on M (one TMEM lane each)
-// An N tile is 8 sites = 168 columns + 8 zero columns (UMMA N = 176); each of the 8 epilogue warps owns 32
+// An N tile is 8 sites in two halves of 4 x 21 + 4 zero columns (UMMA N = 176); each of the 8 epilogue warps owns 32
 // sequences x 4 sites, so a thread sees whole 21-state logit vectors of its sequence: +h, softmax, fx,
 // residuals, bf16 hi/lo split written transposed (sequence fastest) straight into the operand of the backward
 // GEMM.  The 847 MB logits matrix never exists.  Per-(site, 32-sequence group) partials of g_h / fx keep the
@@ -521,8 +521,9 @@ __global__ void expand_tcf_kernel(const float *__restrict__ x, __nv_bfloat16 *__
     const int i = blockIdx.y, j = blockIdx.x;
     if (j <= i) return;
     const float *J = x + (int64_t)L * q + ((int64_t)i * (2 * L - i - 1) / 2 + (j - i - 1)) * q * q;
-    const int64_t ri = (int64_t)(i / TF_SITES) * TF_BN + (i % TF_SITES) * 21;     // padded row base of site i
-    const int64_t rj = (int64_t)(j / TF_SITES) * TF_BN + (j % TF_SITES) * 21;
+    // padded row base of a site: tile of 8 sites = two halves of 88 rows (4 sites x 21 states + 4 zero rows)
+    const int64_t ri = (int64_t)(i / TF_SITES) * TF_BN + ((i % TF_SITES) / 4) * 88 + (i % 4) * 21;
+    const int64_t rj = (int64_t)(j / TF_SITES) * TF_BN + ((j % TF_SITES) / 4) * 88 + (j % 4) * 21;
     for (int e = threadIdx.x; e < q * q; e += blockDim.x) {
         const int a = e / q, b = e - a * q;
         const float v = J[e];
