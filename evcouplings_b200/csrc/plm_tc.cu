@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -112,6 +114,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (TS form): the shared operand of the hi/lo MMA pair is copied smem -> TMEM once
+// (tcgen05.cp, 128 lanes x 256 bit = one K=16 slice) and both MMAs read it from there, which removes ~45 % of
+// the shared-memory operand traffic that bounds the SS form at M128 x N<=192.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -153,7 +172,7 @@ template <int SPLIT_A>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                           const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
-                          int m_tiles, int n_tiles, int num_kb, int k_chunk)
+                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int a_tmem)
 {
     // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
     // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
@@ -236,6 +255,21 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
                     const uint64_t d0 = make_desc_sw128(st);
                     const uint64_t d1 = make_desc_sw128(st + BYTES0);
                     const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
+                    if (!SPLIT_A && a_tmem) {
+                        // stage the shared A tile of this k-block in TMEM (columns 384 + 32*s ..), 8 columns per K=16
+                        const uint32_t ta = tmem_base + 2u * TC_BN + (uint32_t)(s * 32);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)
+                            tmem_cp_128x256b(ta + (uint32_t)(k * 8), d0 + (uint64_t)((k * 16 * 2) >> 4));
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++) {
+                            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                            umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), d1 + koff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), d2 + koff, idesc, 1u);
+                        }
+                        umma_commit(&empty[s]);
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++) {
                         const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
@@ -364,7 +398,7 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     const uint32_t *__restrict__ msa4, const float *__restrict__ wts,
                     __nv_bfloat16 *__restrict__ Rt_hi, __nv_bfloat16 *__restrict__ Rt_lo, int64_t Kp,
                     float *__restrict__ gh_part, double *__restrict__ fx_part, PlmGeom g, int m_tiles, int n_tiles,
-                    int num_kb)
+                    int num_kb, int a_tmem)
 {
     constexpr int Q = 21;                          // states per site of this instantiation (q = 21 or 20 -> S = 21)
     extern __shared__ unsigned char smem_dyn[];
@@ -432,11 +466,24 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 const uint64_t da = make_desc_sw128(st);
                 const uint64_t dh = make_desc_sw128(st + TC_A_BYTES);
                 const uint64_t dl = make_desc_sw128(st + TC_A_BYTES + TF_B_BYTES);
+                if (a_tmem) {
+                    const uint32_t ta = tmem_base + 2u * TF_BN + (uint32_t)(s * 32);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; k++) {
-                    const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                    umma_bf16(tmem_d, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_bf16(tmem_d, da + koff, dl + koff, idesc, 1u);
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        tmem_cp_128x256b(ta + (uint32_t)(k * 8), da + (uint64_t)((k * 16 * 2) >> 4));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                        umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), dl + koff, idesc, 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                        umma_bf16(tmem_d, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_d, da + koff, dl + koff, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty[s]);
             }
@@ -659,6 +706,16 @@ __global__ void finalize_pairs_tc_kernel(const float *__restrict__ Gd, float *__
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
+static int a_tmem_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("EVC_A_TMEM");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 static int sm_count_cached()
 {
     static int n = 0;
@@ -739,7 +796,7 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Np / TC_BN);
     const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
-                                                                (int)(t.Kp / TC_BK), TC_K_CHUNK);
+                                                                (int)(t.Kp / TC_BK), TC_K_CHUNK, a_tmem_enabled());
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -802,7 +859,7 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
     const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
     const int num_kb = (int)(t.Kw / TC_BK);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
-                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK);
+                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK, 0);
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -867,7 +924,7 @@ int plm_tcff_forward(const PlmGeom &g, const PlmTcffGeom &t, const void *maps, c
     tc_fwd_fused_kernel<<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_x, d_msa4, d_wts,
                                                         reinterpret_cast<__nv_bfloat16 *>(d_rt_hi),
                                                         reinterpret_cast<__nv_bfloat16 *>(d_rt_lo), Kp, d_gh_part,
-                                                        d_fx_part, g, t.m_tiles, t.n_tiles, (int)(t.Kw / TC_BK));
+                                                        d_fx_part, g, t.m_tiles, t.n_tiles, (int)(t.Kw / TC_BK), a_tmem_enabled());
     EVC_KERNEL_CHECK();
     return 0;
 }
