@@ -366,7 +366,9 @@ int evc_plm_set_forward(evc_plm_t *h, int32_t mode)
         return 1;
     }
     EVC_CUDA(cudaSetDevice(h->device));
-    if (mode == 2 && !plm_tcff_supported(h->g)) mode = 1;     // nucleotide alphabets: unfused tensor-core forward
+    // the fused variant needs the 21-wide site layout and keeps the whole K extent in one TMEM accumulation
+    // chain (no K-chunk promotion): nucleotide alphabets and L*q > 8192 use the unfused tensor-core forward
+    if (mode == 2 && (!plm_tcff_supported(h->g) || (int64_t)h->g.L * h->g.q > 8192)) mode = 1;
     if (mode >= 1) {
         if (evc_plm_set_backward(h, 1)) return 1;     // the tensor-core forward feeds the tensor-core backward
         if (!h->d_x1h) {

@@ -197,7 +197,7 @@ def test_plm_eval_tensor_core_forward_vs_oracle(lib, N, L, q, gap, seed, xscale)
 def test_plm_eval_large_L_shapes(lib, N, L, q, gap, seed):
     """geometry of the long-alignment configs (more sites than one shared-memory row block / many GEMM tiles)"""
     _check_eval(lib, N, L, q, gap, seed, tcf=True)
-    _check_eval(lib, N, L, q, gap, seed, tcf=True, fused=True)
+    _check_eval(lib, N, L, q, gap, seed, tcf=True, fused=True)      # falls back to the unfused path for L*q > 8192
     _check_eval(lib, N, L, q, gap, seed, tc=False, tcf=False)
 
 
