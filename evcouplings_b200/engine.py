@@ -262,11 +262,17 @@ class CudaPlmProblem(object):
         return self.x.cpu().numpy()
 
     def norms(self):
-        """(|h|, |J|) of the current parameters (for the iteration table)."""
+        """(|h|, |J|) of the current parameters (for the iteration table), via the library's dot kernels."""
+        import math
+        e = self.engine
         nh = self.L * self.q
-        h = self.x[:nh].double()
-        J = self.x[nh:].double()
-        return float(h.norm().item()), float(J.norm().item())
+        out = []
+        for lo, n in ((0, nh), (nh, self.n - nh)):
+            v = self.x[lo:lo + n]
+            _lib.check(self.lib.evc_vec_dot(e.ptr(v), e.ptr(v), n, e.ptr(self.dotbuf), e.stream()), "evc_vec_dot")
+            e.kernel_launches += 2
+            out.append(math.sqrt(float(self.dotbuf.item())))
+        return out[0], out[1]
 
     def fit(self, x0, params, progress=None):
         self.set_x(x0)
