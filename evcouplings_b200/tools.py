@@ -193,9 +193,11 @@ def run_plmc(alignment, couplings_file, param_file=None,
         log.append("%d sites out of %d" % (L, ali.num_total_sites))
         log.append("Region starts at %d" % ali.region_start)
 
+    t0 = time.time()
     if engine is None:
         engine = _default_engine()
     rank = getattr(engine, "rank", 0)
+    run.timings["engine_init_s"] = time.time() - t0
 
     # (b) sequence reweighting
     t0 = time.time()
@@ -211,8 +213,10 @@ def run_plmc(alignment, couplings_file, param_file=None,
                % (n_eff, 100.0 * theta, scale))
 
     # (a) PLM inference
+    t0 = time.time()
     problem = engine.plm_problem(ali.codes, weights.astype(np.float32), q, ali.gap_code, lambda_h, lambda_J,
                                  m=history)
+    run.timings["problem_setup_s"] = time.time() - t0
     try:
         t0 = time.time()
         fi_counts, fij_counts = problem.weighted_counts()
@@ -245,6 +249,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
     h = x[:L * q].reshape(L, q)
     J = x[L * q:].reshape(L * (L - 1) // 2, q, q)
 
+    t0 = time.time()
     if rank == 0:
         run.cn = model_io.write_ec_file(couplings_file, fn, L, ali.index_list, ali.target_seq)
         if param_file is not None:
@@ -256,6 +261,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
                 param_file, L, q, ali.n_valid, ali.n_total - ali.n_valid, int(res.iterations),
                 1.0 - theta, lambda_h, lambda_J, 0.0, n_eff, ali.model_alphabet, w_all,
                 ali.target_seq, ali.index_list, fi, h, fij, J)
+    run.timings["write_files_s"] = time.time() - t0
     run.log = "\n".join(log) + "\n"
     run.timings["total_s"] = time.time() - t_start
 
