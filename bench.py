@@ -326,7 +326,11 @@ def run_hamming(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    if "EVC_NCCL_DEBUG" not in os.environ:      # keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/null"
     if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from evcouplings_b200 import msa, synthetic, _lib
     from evcouplings_b200.engine import CudaEngine, shard_bounds
