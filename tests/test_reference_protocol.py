@@ -108,3 +108,16 @@ def test_reference_parse_of_realistic_failure_modes(ref):
         ref["ct"].parse_plmc_log("nothing useful")
     with pytest.raises(KeyError):
         tools.parse_plmc_log("nothing useful")
+
+
+def test_product_ingest_on_real_pabp_alignment(golden_dir):
+    """product ingest on the real A2M shipped with the reference == the golden fixture (which the oracle's
+    per-character restatement produced and plmc's own header / weights confirm: 151,496 valid + 545 invalid)."""
+    from evcouplings_b200 import msa
+    path = os.path.join(ref_harness.REFERENCE_ROOT, "notebooks", "example", "PABP_YEAST.a2m")
+    ali = msa.load_alignment(path, focus="PABP_YEAST", ignore_gaps=True)
+    c = np.load(os.path.join(golden_dir, "pabp_codes.npz"))
+    valid = np.unpackbits(c["valid_packed"])[: int(c["n_total"])].astype(bool)
+    assert np.array_equal(ali.codes, c["codes"]) and np.array_equal(ali.valid, valid)
+    assert ali.target_seq == str(c["target_seq"]) and np.array_equal(ali.index_list, c["index_list"])
+    assert (ali.n_valid, ali.n_total - ali.n_valid, ali.region_start, ali.num_total_sites) == (151496, 545, 115, 96)
