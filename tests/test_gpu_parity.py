@@ -584,3 +584,22 @@ def test_hamiltonians_and_mutants_vs_reference(engine, golden_dir):
     hj = sum(J[i, j, big[k, i], big[k, j]] for i in range(82) for j in range(i + 1, 82))
     hh = sum(models["pabp"]["h"][i, big[k, i]] for i in range(82))
     assert abs(Hb[k, 1] - hj) < 2e-4 * max(1.0, abs(hj)) and abs(Hb[k, 2] - hh) < 1e-4
+
+
+def test_plmc_compatible_executable_on_gpu(tmp_path):
+    """bin/evcplm-plmc with the argv the reference builds (tools.py:202-262): files written, stderr parses"""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    codes = synthetic.synthetic_msa_codes(200, 40, 1)
+    a2m = str(tmp_path / "cfg1.a2m")
+    synthetic.write_a2m(a2m, codes)
+    ecs, model = str(tmp_path / "o_ECs.txt"), str(tmp_path / "o.model")
+    cmd = [sys.executable, os.path.join(root, "bin", "evcplm-plmc"), "-c", ecs, "-o", model, "-f", "seq0", "-g",
+           "-m", "25", "-t", "0.2", "-lh", "0.01", "-le", "7.41", "-n", "8", a2m]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    it, fields = tools.parse_plmc_log(p.stderr)
+    assert fields[1:6] == (200, 200, 40, 40, 1) and len(it) == 25
+    m = po.read_model(model)
+    assert (m["L"], m["q"], m["num_iter"]) == (40, 20, 25) and abs(m["lambda_J"] - 7.41) < 1e-5
+    assert len(open(ecs).read().strip().split("\n")) == 780

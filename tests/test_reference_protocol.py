@@ -121,3 +121,48 @@ def test_product_ingest_on_real_pabp_alignment(golden_dir):
     assert np.array_equal(ali.codes, c["codes"]) and np.array_equal(ali.valid, valid)
     assert ali.target_seq == str(c["target_seq"]) and np.array_equal(ali.index_list, c["index_list"])
     assert (ali.n_valid, ali.n_total - ali.n_valid, ali.region_start, ali.num_total_sites) == (151496, 545, 115, 96)
+
+
+def test_unmodified_reference_run_plmc_over_plmc_compatible_cli(ref, tmp_path):
+    """Secondary plug point: the reference's OWN run_plmc (tools.py:126-307: argv, subprocess, stderr parsing,
+    output checks) drives our plmc-compatible executable.  The wrapper used here injects the test-only oracle
+    engine (no GPU in this container); bin/evcplm-plmc is the same entry point with the CUDA engine."""
+    import stat
+    import sys as _sys
+    from evcouplings_b200 import synthetic
+    from oracle import plm_oracle as po
+    codes = synthetic.synthetic_msa_codes(150, 16, 3)
+    a2m = str(tmp_path / "in.a2m")
+    synthetic.write_a2m(a2m, codes)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    wrapper = tmp_path / "plmc_test_wrapper"
+    wrapper.write_text(
+        "#!%s\nimport sys\nsys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from cpu_engine import OracleEngine\nfrom evcouplings_b200.plmc_cli import main\n"
+        "sys.exit(main(engine=OracleEngine()))\n" % (_sys.executable, root, os.path.join(root, "tests")))
+    wrapper.chmod(wrapper.stat().st_mode | stat.S_IEXEC)
+    ecs, model = str(tmp_path / "o" / "x_ECs.txt"), str(tmp_path / "o" / "x.model")
+    res = ref["ct"].run_plmc(a2m, ecs, model, focus_seq="seq0/1-16", alphabet=None, theta=0.8, scale=None,
+                             ignore_gaps=True, iterations=12, lambda_h=0.01, lambda_J=2.5, lambda_g=None, cpu=2,
+                             binary=str(wrapper))
+    assert res.num_valid_seqs == 150 and res.num_total_seqs == 150 and res.num_valid_sites == 16
+    assert res.focus_seq_index == 1 and res.region_start == 1
+    assert res.optimization_status == "LBFGSERR_MAXIMUMITERATION" and len(res.iteration_table) == 12
+    m = po.read_model(model)
+    assert (m["L"], m["q"], m["num_iter"]) == (16, 20, 12) and abs(m["theta"] - 0.2) < 1e-6
+    assert abs(m["lambda_J"] - 2.5) < 1e-6 and abs(res.effective_samples - m["n_eff"]) < 0.06
+    assert len(open(ecs).read().strip().split("\n")) == 16 * 15 // 2
+
+
+def test_plmc_cli_argument_handling():
+    from evcouplings_b200 import plmc_cli
+    ali, o = plmc_cli.parse_args(["-c", "e.txt", "-o", "m.model", "-f", "SEQ", "-g", "-m", "100", "-t", "0.2",
+                                  "-lh", "0.01", "-le", "16.2", "-n", "4", "in.a2m"])
+    assert ali == "in.a2m" and o["couplings_file"] == "e.txt" and o["param_file"] == "m.model"
+    assert o["focus_seq"] == "SEQ" and o["ignore_gaps"] and o["iterations"] == 100
+    assert abs(o["theta"] - 0.8) < 1e-12 and o["lambda_h"] == 0.01 and o["lambda_J"] == 16.2 and o["cpu"] == "4"
+    import io
+    for bad in (["-c"], ["in.a2m"], ["-c", "e", "a", "b"], ["-zz", "1", "-c", "e", "a"]):
+        assert plmc_cli.main(bad, stderr=io.StringIO()) == 2
+    err = io.StringIO()
+    assert plmc_cli.main(["-c", "/tmp/e.txt", "/nonexistent/file.a2m"], stderr=err) == 1 and "ResourceError" in err.getvalue()
