@@ -166,3 +166,37 @@ def test_plmc_cli_argument_handling():
         assert plmc_cli.main(bad, stderr=io.StringIO()) == 2
     err = io.StringIO()
     assert plmc_cli.main(["-c", "/tmp/e.txt", "/nonexistent/file.a2m"], stderr=err) == 1 and "ResourceError" in err.getvalue()
+
+
+def test_reference_complex_protocol_over_our_run_plmc(ref, tmp_path):
+    """BASELINE configs[4] flavour (EVcomplex concatenated two-chain alignment): the reference's ``complex``
+    protocol (protocol.py:480-594; same infer_plmc -> run_plmc boundary, two segments, inter-chain EC table)
+    runs unmodified over our run_plmc.  Small shapes here (2 x 12 sites); the engine itself is parity- and
+    bench-tested at L=800 on the GPU."""
+    import pandas as pd
+    from evcouplings_b200 import synthetic, tools
+    from cpu_engine import OracleEngine
+    N, L1, L2 = 160, 12, 12
+    L = L1 + L2
+    codes = synthetic.synthetic_msa_codes(N, L, 8)
+    a2m = str(tmp_path / "complex.a2m")
+    synthetic.write_a2m(a2m, codes, focus_name="A_B")          # header "A_B/1-24" like complex/alignment.py:85-92
+    ct = ref["ct"]
+    original = ct.run_plmc
+    ct.run_plmc = lambda *a, **k: tools.run_plmc(*a, engine=OracleEngine(), **k)
+    try:
+        prefix = str(tmp_path / "cx" / "job")
+        kw = _kwargs(prefix, a2m, L, True)
+        kw.update(protocol="complex", focus_sequence="A_B/1-%d" % L, use_all_ecs_for_scoring=False,
+                  segments=[["A_1", "aa", "A", 1, L1, list(range(1, L1 + 1))],
+                            ["B_1", "aa", "B", 1, L2, list(range(1, L2 + 1))]])
+        outcfg = ref["cpr"].run(**kw)
+    finally:
+        ct.run_plmc = original
+    assert outcfg["num_sites"] == L and outcfg["num_valid_sequences"] == N
+    inter = pd.read_csv(outcfg["inter_ec_file"])
+    assert len(inter) == L1 * L2 and set(inter["segment_i"]) == {"A_1"} and set(inter["segment_j"]) == {"B_1"}
+    allecs = pd.read_csv(outcfg["ec_file"])
+    assert {"i", "j", "segment_i", "segment_j", "cn", "probability"} <= set(allecs.columns)
+    model = ref["cm"].CouplingsModel(outcfg["model_file"])
+    assert model.L == L and model.num_symbols == 20
