@@ -286,7 +286,10 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None,
+        "dtype": "f32" if (prob.forward == "gather" and prob.backward == "gather") else
+                 "f32 parameters/accumulation; tensor-core products as bf16 hi+lo pairs (16 mantissa bits)",
+        "data": "synthetic",
         "config": {"workload": ("PLM fx+gradient, synthetic MSA N=%d%s L=%d q=%d fp32"
                                 % (N_PER_GPU, " per GPU (sharded, N_total=%d)" % n_total if world > 1 else "", L, Q))
                    + (" (BASELINE configs[1])" if (N_PER_GPU, L) == (50000, 200) else " (non-default shape)"),
@@ -305,6 +308,26 @@ def run_b200(args):
                           "note": "includes H2D + packing; untimed setup, not the benchmarked step"},
     }
     if rank == 0 and world == 1:
+        # accuracy of the timed path, on a bounded sample, against the float64 oracle (checker only)
+        try:
+            from oracle import c_oracle as co
+            ns = min(CPU_SAMPLE_N, n_total)
+            sub = engine.plm_problem(codes[:ns], weights[:ns], Q, -1, 0.0, 0.0, backward=prob.backward,
+                                     forward=prob.forward)
+            sub.set_x(x)
+            fs = sub.evaluate(sub.x)
+            gs = sub.g.cpu().numpy().astype(np.float64)
+            sub.close()
+            f64, g64, _ = co.plm_eval(codes[:ns], weights[:ns].astype(np.float64), x.astype(np.float64), Q, 0.0, 0.0, "f64")
+            _, g32, _ = co.plm_eval(codes[:ns], weights[:ns], x, Q, 0.0, 0.0, "f32")
+            line["accuracy"] = {
+                "sample": "%d sequences of the workload, data term only, vs float64 oracle" % ns,
+                "grad_rel_l2_err": float(np.linalg.norm(gs - g64) / np.linalg.norm(g64)),
+                "fx_rel_err": float(abs(fs - f64) / abs(f64)),
+                "cpu_fp32_port_grad_rel_l2_err": float(np.linalg.norm(g32 - g64) / np.linalg.norm(g64)),
+            }
+        except Exception as e:      # the checker must never break the bench line
+            line["accuracy"] = {"error": str(e)}
         cb_value, cb_dt, threads = cpu_arm(codes, x, weights, 2, 1, CPU_SAMPLE_N)
         line["cpu_baseline"] = {"value": cb_value, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%d of the %d sequences, 2 timed evaluations after 1 warm-up (%.2f s each)"
