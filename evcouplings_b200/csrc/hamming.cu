@@ -83,6 +83,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
         for (int c = 0; c < 8; c++) cnt[r][c] = 0;
     if (tid < HT) { s_rsum[tid] = 0; s_csum[tid] = 0; }
 
+    bool dead = false;
     for (int w0 = 0; w0 < W; w0 += HWC) {
         const int nw = min(HWC, W - w0);
         __syncthreads();
@@ -123,7 +124,20 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
                     for (int p = 1; p < HP; p++) d |= a[p][r] ^ b[p][c];
                     cnt[r][c] += __popc(~d);
                 }
+            // exact early termination: after word w a pair can still gain at most 32 * (W - 1 - w) identities;
+            // when no pair of the whole tile can reach the threshold any more the remaining words are skipped
+            const int wdone = w0 + ww;
+            if ((wdone & 1) && wdone + 1 < W) {
+                const int need = thr - 32 * (W - 1 - wdone);
+                int alive = 0;
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+#pragma unroll
+                    for (int c = 0; c < 8; c++) alive |= (cnt[r][c] >= need);
+                if (!__syncthreads_or(alive)) { dead = true; break; }
+            }
         }
+        if (dead) break;
     }
 
     // threshold -> neighbour flags; credit rows (always) and columns (off-diagonal tiles)
