@@ -83,10 +83,13 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
         for (int c = 0; c < 8; c++) cnt[r][c] = 0;
     if (tid < HT) { s_rsum[tid] = 0; s_csum[tid] = 0; }
 
-    bool dead = false;
+    // Exact early termination at warp granularity: after word w a pair can still gain at most 32 * (W - 1 - w)
+    // identities; a warp (16 x 128 pairs) whose pairs can no longer reach the threshold stops comparing (it only
+    // keeps arriving at the staging barriers), and the tile ends when all of its warps are done.
+    bool wdead = false;
     for (int w0 = 0; w0 < W; w0 += HWC) {
         const int nw = min(HWC, W - w0);
-        __syncthreads();
+        if (!__syncthreads_or(!wdead)) break;
         // stage nw words x 5 planes x 128 sequences for both sides
         for (int e = tid; e < HWC * HP * HT; e += 256) {
             const int s = e & (HT - 1);
@@ -102,7 +105,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
             s_col[ww][p][s] = vc;
         }
         __syncthreads();
-        for (int ww = 0; ww < nw; ww++) {
+        for (int ww = 0; ww < nw && !wdead; ww++) {
             uint32_t a[HP][8], b[HP][8];
 #pragma unroll
             for (int p = 0; p < HP; p++) {
@@ -124,20 +127,17 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
                     for (int p = 1; p < HP; p++) d |= a[p][r] ^ b[p][c];
                     cnt[r][c] += __popc(~d);
                 }
-            // exact early termination: after word w a pair can still gain at most 32 * (W - 1 - w) identities;
-            // when no pair of the whole tile can reach the threshold any more the remaining words are skipped
             const int wdone = w0 + ww;
-            if ((wdone & 1) && wdone + 1 < W) {
+            if (wdone >= 1 && wdone + 1 < W) {
                 const int need = thr - 32 * (W - 1 - wdone);
                 int alive = 0;
 #pragma unroll
                 for (int r = 0; r < 8; r++)
 #pragma unroll
                     for (int c = 0; c < 8; c++) alive |= (cnt[r][c] >= need);
-                if (!__syncthreads_or(alive)) { dead = true; break; }
+                if (!__any_sync(0xffffffffu, alive)) wdead = true;
             }
         }
-        if (dead) break;
     }
 
     // threshold -> neighbour flags; credit rows (always) and columns (off-diagonal tiles)
