@@ -18,6 +18,10 @@
 // 8x8 pair counters per thread in registers, plane words staged in shared
 // memory 16 words (512 sites) at a time.  The plane buffer (N * 5 * W * 4 bytes; 40 MB at
 // N=200k, L=300) is L2-resident, so the kernel is bound by the integer pipes.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -60,9 +64,16 @@ __device__ __forceinline__ void tile_from_index(int64_t idx, int64_t T, int64_t 
     C = r + (idx - (r * T - r * (r - 1) / 2));
 }
 
+// FILTER = false: full comparison, neighbour counts credited directly (with exact early termination).
+// FILTER = true : phase 1 of the two-phase scheme -- only the first W1 plane words are compared; a pair whose
+//                 identities so far plus everything it could still gain reach the threshold is appended to a
+//                 candidate list (row, col | credit-both flag) for exact verification by hamming_verify_kernel.
+template <bool FILTER>
 __global__ void __launch_bounds__(256, 2)
 hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int thr,
-                    int64_t tile_begin, int64_t T, int *__restrict__ counts)
+                    int64_t tile_begin, int64_t T, int *__restrict__ counts, int W1,
+                    uint2 *__restrict__ cand, unsigned long long *__restrict__ cand_count,
+                    unsigned long long cand_cap)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t (*s_row)[HP][HT] = reinterpret_cast<uint32_t (*)[HP][HT]>(s_dyn);
@@ -87,8 +98,9 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
     // identities; a warp (16 x 128 pairs) whose pairs can no longer reach the threshold stops comparing (it only
     // keeps arriving at the staging barriers), and the tile ends when all of its warps are done.
     bool wdead = false;
-    for (int w0 = 0; w0 < W; w0 += HWC) {
-        const int nw = min(HWC, W - w0);
+    const int Wrun = FILTER ? W1 : W;
+    for (int w0 = 0; w0 < Wrun; w0 += HWC) {
+        const int nw = min(HWC, Wrun - w0);
         if (!__syncthreads_or(!wdead)) break;
         // stage nw words x 5 planes x 128 sequences for both sides
         for (int e = tid; e < HWC * HP * HT; e += 256) {
@@ -128,7 +140,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
                     cnt[r][c] += __popc(~d);
                 }
             const int wdone = w0 + ww;
-            if (wdone >= 1 && wdone + 1 < W) {
+            if (!FILTER && wdone >= 1 && wdone + 1 < W) {
                 const int need = thr - 32 * (W - 1 - wdone);
                 int alive = 0;
 #pragma unroll
@@ -140,8 +152,24 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
         }
     }
 
-    // threshold -> neighbour flags; credit rows (always) and columns (off-diagonal tiles)
     const bool diag = (R == C);
+    if (FILTER) {
+        // candidates: identities in the first W1 words + the 32 * (W - W1) still possible >= threshold
+        const int need = thr - 32 * (W - W1);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int64_t gr = row0 + ty * 8 + r, gc = col0 + tx * 8 + c;
+                if (gr < N && gc < N && cnt[r][c] >= need) {
+                    const unsigned long long slot = atomicAdd(cand_count, 1ull);
+                    if (slot < cand_cap)
+                        cand[slot] = make_uint2((unsigned)gr, (unsigned)gc | (diag ? 0u : 0x80000000u));
+                }
+            }
+        return;
+    }
+    // threshold -> neighbour flags; credit rows (always) and columns (off-diagonal tiles)
     int rs[8], cs[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) rs[r] = 0;
@@ -173,6 +201,63 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
     }
 }
 
+// phase 2: exact identity count of every candidate pair over all W words (thread = candidate)
+__global__ void hamming_verify_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int thr,
+                                      const uint2 *__restrict__ cand, unsigned long long ncand,
+                                      int *__restrict__ counts)
+{
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncand) return;
+    const uint2 pr = cand[k];
+    const int64_t r = pr.x, c = pr.y & 0x7fffffffu;
+    const bool both = (pr.y & 0x80000000u) != 0;
+    int cnt = 0;
+    for (int w = 0; w < W; w++) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int p = 0; p < HP; p++) {
+            const int64_t base = ((int64_t)p * W + w) * N;
+            d |= planes[base + r] ^ planes[base + c];
+        }
+        cnt += __popc(~d);
+    }
+    if (cnt >= thr) {
+        atomicAdd(&counts[r], 1);
+        if (both) atomicAdd(&counts[c], 1);
+    }
+}
+
+struct HammingScratch {
+    uint2 *cand = nullptr;
+    unsigned long long *count = nullptr;
+    unsigned long long cap = 0;
+};
+static HammingScratch g_hs[64];
+
+static int hamming_scratch(unsigned long long want, HammingScratch **out)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("hamming: bad device"); return 1; }
+    HammingScratch &h = g_hs[dev];
+    if (!h.count && cudaMalloc(&h.count, sizeof(unsigned long long)) != cudaSuccess) {
+        set_error("hamming: scratch allocation failed");
+        return 1;
+    }
+    if (h.cap < want) {
+        cudaFree(h.cand);
+        h.cand = nullptr;
+        h.cap = 0;
+        if (cudaMalloc(&h.cand, want * sizeof(uint2)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("hamming: candidate buffer allocation failed");
+            return 1;
+        }
+        h.cap = want;
+    }
+    *out = &h;
+    return 0;
+}
+
 int64_t hamming_plane_words(int64_t N, int L) { return (int64_t)HP * ceil_div(L, 32) * N; }
 
 int64_t hamming_num_tiles(int64_t N)
@@ -201,12 +286,49 @@ int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_iden
         return 1;
     }
     const size_t smem = (size_t)2 * HWC * HP * HT * sizeof(uint32_t);
-    EVC_CUDA(cudaFuncSetAttribute(hamming_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVC_CUDA(cudaFuncSetAttribute(hamming_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVC_CUDA(cudaFuncSetAttribute(hamming_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int thr = min_identical + (W * 32 - L);   // padded sites always "agree"
+    const int64_t ntile = tile_end - tile_begin;
+    if (ntile == 0) return 0;
+
+    // Two-phase scheme for long alignments: filter on the first ~30 % of the words, verify the survivors.
+    // The filter only pays when it can reject: the identities still obtainable after W1 words, 32 * (W - W1),
+    // must be well below the threshold.  Falls back to the single-phase kernel if the candidate list overflows.
+    const int W1 = (W * 3 + 9) / 10;
+    const bool two_phase = W >= 6 && (thr - 32 * (W - W1)) >= 8 && getenv("EVC_HAMMING_SINGLE_PHASE") == nullptr;
+    if (two_phase) {
+        HammingScratch *hs = nullptr;
+        unsigned long long want = (unsigned long long)std::min<int64_t>((int64_t)1 << 27, std::max<int64_t>(N * 512, 1 << 20));
+        if (hamming_scratch(want, &hs) == 0) {
+            EVC_CUDA(cudaMemsetAsync(hs->count, 0, sizeof(unsigned long long), st));
+            int64_t done = tile_begin;
+            while (done < tile_end) {
+                const int64_t nblk = std::min<int64_t>(tile_end - done, (int64_t)1 << 30);
+                hamming_tile_kernel<true><<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts, W1,
+                                                                             hs->cand, hs->count, hs->cap);
+                EVC_KERNEL_CHECK();
+                done += nblk;
+            }
+            unsigned long long ncand = 0;
+            EVC_CUDA(cudaMemcpyAsync(&ncand, hs->count, sizeof(ncand), cudaMemcpyDeviceToHost, st));
+            EVC_CUDA(cudaStreamSynchronize(st));
+            if (ncand <= hs->cap) {
+                if (ncand > 0) {
+                    hamming_verify_kernel<<<(unsigned)((ncand + 255) / 256), 256, 0, st>>>(d_planes, N, W, thr, hs->cand,
+                                                                                           ncand, d_counts);
+                    EVC_KERNEL_CHECK();
+                }
+                return 0;
+            }
+            // overflow: nothing has been credited yet (the filter never touches counts) -> single phase below
+        }
+    }
     int64_t done = tile_begin;
     while (done < tile_end) {                        // grid.x limit 2^31-1
-        const int64_t nblk = (tile_end - done) < (int64_t)1 << 30 ? (tile_end - done) : (int64_t)1 << 30;
-        hamming_tile_kernel<<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts);
+        const int64_t nblk = std::min<int64_t>(tile_end - done, (int64_t)1 << 30);
+        hamming_tile_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts, W, nullptr,
+                                                                      nullptr, 0);
         EVC_KERNEL_CHECK();
         done += nblk;
     }
