@@ -154,17 +154,37 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
 
     const bool diag = (R == C);
     if (FILTER) {
-        // candidates: identities in the first W1 words + the 32 * (W - W1) still possible >= threshold
+        // candidates: identities in the first W1 words + the 32 * (W - W1) still possible >= threshold.
+        // One atomic per warp: lane-local counts -> warp prefix sum -> the warp reserves a contiguous range.
         const int need = thr - 32 * (W - W1);
+        int mine = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                mine += (row0 + ty * 8 + r < N && col0 + tx * 8 + c < N && cnt[r][c] >= need) ? 1 : 0;
+        const int lane = tid & 31;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) return;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned long long slot = base + (unsigned long long)(incl - mine);
 #pragma unroll
         for (int r = 0; r < 8; r++)
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const int64_t gr = row0 + ty * 8 + r, gc = col0 + tx * 8 + c;
                 if (gr < N && gc < N && cnt[r][c] >= need) {
-                    const unsigned long long slot = atomicAdd(cand_count, 1ull);
                     if (slot < cand_cap)
                         cand[slot] = make_uint2((unsigned)gr, (unsigned)gc | (diag ? 0u : 0x80000000u));
+                    slot++;
                 }
             }
         return;
