@@ -168,11 +168,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Tile enumeration: M tiles are swept in groups of `mgroup`; inside a group the M index is fastest, then the N
+// tile.  For the forward product (SPLIT_A) a group of 11 M tiles = 24 MB of the coupling operand stays L2
+// resident while every sequence tile passes by (the whole 71 MB operand does not: the 126 MB L2 is two
+// partitions); the backward uses one group (all CTAs advance along K together and share operand tiles in time).
+__device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, int mgroup, int &m_tile, int &n_tile)
+{
+    const int full = (m_tiles / mgroup) * mgroup * n_tiles;
+    if (tile < full) {
+        const int per = mgroup * n_tiles;
+        const int g = tile / per, r = tile - g * per;
+        n_tile = r / mgroup;
+        m_tile = g * mgroup + (r - n_tile * mgroup);
+    } else {
+        const int rem = m_tiles % mgroup, r = tile - full;
+        n_tile = r / rem;
+        m_tile = (m_tiles / mgroup) * mgroup + (r - n_tile * rem);
+    }
+}
+
 template <int SPLIT_A>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                           const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
-                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int a_tmem)
+                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int a_tmem, int mgroup)
 {
     // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
     // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
@@ -218,7 +237,8 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
         const uint64_t keep = l2_policy_evict_last();
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
+            int m_tile, n_tile;
+            decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
             for (int kb = 0; kb < num_kb; kb++, it++) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
@@ -294,7 +314,8 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
         constexpr int ECOLS = TC_BN / 2;        // 96 columns per epilogue warp
         int wl = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
+            int m_tile, n_tile;
+            decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
             const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
             float *out = D + row * ldd + (int64_t)n_tile * TC_BN + ehalf * ECOLS;
             // chunk sums are promoted into registers (IEEE round-to-nearest adds); one store per tile
@@ -796,7 +817,7 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Np / TC_BN);
     const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
-                                                                (int)(t.Kp / TC_BK), TC_K_CHUNK, a_tmem_enabled());
+                                                                (int)(t.Kp / TC_BK), TC_K_CHUNK, a_tmem_enabled(), m_tiles);
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -859,7 +880,7 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
     const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
     const int num_kb = (int)(t.Kw / TC_BK);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
-                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK, 0);
+                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK, 0, std::min(m_tiles, 11));
     EVC_KERNEL_CHECK();
     return 0;
 }
