@@ -261,6 +261,9 @@ def run_plmc(alignment, couplings_file, param_file=None,
                 param_file, L, q, ali.n_valid, ali.n_total - ali.n_valid, int(res.iterations),
                 1.0 - theta, lambda_h, lambda_J, 0.0, n_eff, ali.model_alphabet, w_all,
                 ali.target_seq, ali.index_list, fi, h, fij, J)
+    coll = getattr(engine, "coll", None)
+    if coll is not None:
+        coll.barrier()          # multi-GPU: every rank returns only after rank 0 has written the files
     run.timings["write_files_s"] = time.time() - t0
     run.log = "\n".join(log) + "\n"
     run.timings["total_s"] = time.time() - t_start
