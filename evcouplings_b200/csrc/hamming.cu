@@ -263,7 +263,7 @@ static int hamming_scratch(unsigned long long want, HammingScratch **out)
         set_error("hamming: scratch allocation failed");
         return 1;
     }
-    if (h.cap < want) {
+    if (h.cap < want || getenv("EVC_HAMMING_CAND_CAP") != nullptr) {
         cudaFree(h.cand);
         h.cand = nullptr;
         h.cap = 0;
@@ -320,20 +320,21 @@ int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_iden
     if (two_phase) {
         HammingScratch *hs = nullptr;
         unsigned long long want = (unsigned long long)std::min<int64_t>((int64_t)1 << 27, std::max<int64_t>(N * 512, 1 << 20));
+        if (const char *e = getenv("EVC_HAMMING_CAND_CAP")) want = (unsigned long long)std::max(1ll, atoll(e));   // tests
         if (hamming_scratch(want, &hs) == 0) {
             EVC_CUDA(cudaMemsetAsync(hs->count, 0, sizeof(unsigned long long), st));
             int64_t done = tile_begin;
             while (done < tile_end) {
                 const int64_t nblk = std::min<int64_t>(tile_end - done, (int64_t)1 << 30);
                 hamming_tile_kernel<true><<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts, W1,
-                                                                             hs->cand, hs->count, hs->cap);
+                                                                             hs->cand, hs->count, want);
                 EVC_KERNEL_CHECK();
                 done += nblk;
             }
             unsigned long long ncand = 0;
             EVC_CUDA(cudaMemcpyAsync(&ncand, hs->count, sizeof(ncand), cudaMemcpyDeviceToHost, st));
             EVC_CUDA(cudaStreamSynchronize(st));
-            if (ncand <= hs->cap) {
+            if (ncand <= want) {
                 if (ncand > 0) {
                     hamming_verify_kernel<<<(unsigned)((ncand + 255) / 256), 256, 0, st>>>(d_planes, N, W, thr, hs->cand,
                                                                                            ncand, d_counts);

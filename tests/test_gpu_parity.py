@@ -96,6 +96,27 @@ def test_hamming_edge_thresholds(lib):
     assert (gpu_hamming(lib, hi, 10) == 40).all()
 
 
+def test_hamming_two_phase_overflow_falls_back_exactly(tmp_path):
+    """long alignment (two-phase filter + verify) with a candidate buffer forced to 100 entries: the overflow
+    path must fall back to the single-phase kernel and still be exact (run in a subprocess: env-controlled)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, ctypes, numpy as np; sys.path.insert(0, %r)\n"
+        "from evcouplings_b200 import _lib, msa, synthetic\nfrom oracle import c_oracle as co\n"
+        "lib = _lib.load(); codes = synthetic.synthetic_msa_codes(3000, 300, 6)\n"
+        "thr = msa.identity_threshold_count(0.8, 300); out = np.zeros(3000, dtype=np.int32)\n"
+        "_lib.check(lib.evc_hamming_counts(codes.ctypes.data_as(ctypes.c_void_p), 3000, 300, thr, 0,"
+        " out.ctypes.data_as(ctypes.c_void_p)), 'hamming')\n"
+        "assert np.array_equal(out, co.hamming_counts(codes, thr)); print('exact')\n" % root)
+    for cap in ("100", None):
+        env = dict(os.environ)
+        if cap:
+            env["EVC_HAMMING_CAND_CAP"] = cap
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0 and "exact" in p.stdout, p.stderr[-2000:]
+
+
 def test_hamming_pabp_golden_counts(lib, golden_dir):
     """exact equality with the neighbour counts plmc itself stored (golden PABP run), full 151,496 x 82"""
     c = np.load(os.path.join(golden_dir, "pabp_codes.npz"))
