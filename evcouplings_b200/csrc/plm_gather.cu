@@ -1,4 +1,6 @@
 // Hot path (a): pseudo-likelihood objective + gradient, gather/scatter formulation (sm_100a).
+// (First correct CUDA path and the measured comparison baseline of the tensor-core path in plm_tc.cu; still
+//  used for f_i / f_ij counting, the statistical energies, and selectable with forward/backward = "gather".)
 //
 // Replaces the inner loop of plmc's L-BFGS (reference call
 // site evcouplings/couplings/tools.py:202-266): for every sequence n and site i

@@ -1,28 +1,33 @@
-// Hot path (a), backward as a dense one-hot contraction on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+// Hot path (a) as dense one-hot contractions on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
 //
-// The north star allows tensor cores for the PLL gradient only if the dense recast beats the gather path
-// under ncu; bench.py / profiles/ carry that comparison (the gather backward is kept, see plm_gather.cu).
+// The north star allows tensor cores for the PLL gradient only if the dense recast beats the gather path under
+// ncu; bench.py / profiles/ carry that comparison (the gather kernels are kept, see plm_gather.cu): forward
+// 5.1 ms -> 2.2 + 0.46 ms, backward 15.7 ms -> 2.2 ms at the same parity tolerance.
 //
-// Maths.  With X[n,(j,b)] = [s_nj = b] (one-hot, exact in bf16) and the residuals R[n,(i,a)] = r_ni(a),
-//     Gd[(j,b),(i,a)] = sum_n X[n,(j,b)] * R[n,(i,a)]                      (an (Lq x N) x (N x Lq) GEMM)
-//     g_J(i<j)[a][b]  = Gd[(j,b),(i,a)] + Gd[(i,a),(j,b)]
-// R is split R = R_hi + R_lo with both parts bf16 (hi = rn(r), lo = rn(r - hi)): 16 mantissa bits, relative
-// error 2^-17 per term -- below the fp32 accumulation noise of the sum over ~N/q terms -- and the two
-// products accumulate into the SAME fp32 TMEM accumulator.
+// Maths.  With X[n,(j,b)] = [s_nj = b] (one-hot, exact in bf16), the couplings W[(i,a),(j,b)] = J_ij(a,b) and
+// the residuals R[n,(i,a)] = r_ni(a):
+//     forward   Zt[(i,a), n]     = sum_(j,b) W[(i,a),(j,b)] * X[n,(j,b)]          (logits without h)
+//     backward  Gd[(j,b),(i,a)]  = sum_n     X[n,(j,b)]     * R[n,(i,a)]
+//               g_J(i<j)[a][b]   = Gd[(j,b),(i,a)] + Gd[(i,a),(j,b)]
+// The real-valued operand (W or R) is split in two bf16 terms (hi = rn(v), lo = rn(v - hi)): 16 mantissa bits,
+// relative error 2^-17 per term; both products accumulate into the SAME fp32 TMEM accumulator.
 //
-// Operands (all K-major = sequence index fastest, so the forward kernel writes R^T coalesced):
-//     Xt    [Mp][Kp] bf16   static per MSA           (Mp = Lq rounded to 128, Kp = N rounded to 64)
-//     Rt_hi [Np][Kp] bf16   written by plm_fwd       (Np = Lq rounded to 192)
-//     Rt_lo [Np][Kp] bf16
-//     Gd    [Mp][Np] fp32
-// Kernel: one CTA per 128 x 192 output tile, K loop over all sequences in blocks of 64.
-//     warp 0 (1 thread)  TMA producer: cp.async.bulk.tensor 2-D, SWIZZLE_128B, 3-stage smem ring
-//                        (A 16 KB + B_hi 24 KB + B_lo 24 KB per stage), mbarrier expect_tx
-//     warp 1 (1 thread)  MMA issuer: 4 x 2 tcgen05.mma.cta_group::1.kind::f16 (M128 N192 K16) per stage,
-//                        tcgen05.commit -> "empty" barrier of the stage; final commit -> accumulator ready
-//     warp 2             TMEM allocator (512 columns = two 192-column accumulators)
-//     warps 4..11        epilogue: tcgen05.ld 32x32b.x32 -> chunk sums in registers -> global
-// Roofline: tensor pipe.  2 * 2 * Lq^2 * N flop per evaluation (7.1e12 at N=50k, L=200, q=21).
+// Operands, all K-major (TMA 2-D, SWIZZLE_128B):
+//     forward : Wt_hi, Wt_lo [Mp][Kw] bf16 (written by expand_tc every evaluation), X [Xrows][Kw] bf16 (static)
+//     backward: Xt [Mp][Kp] bf16 (static), Rt_hi, Rt_lo [Np][Kp] bf16 (written by plm_softmax_kernel)
+//
+// tc_gemm_persistent_kernel<SPLIT_A>: one persistent CTA per SM, 128 x 192 tiles, K blocks of 64.
+//     warp 0 (1 thread)  TMA producer, 3-stage shared-memory ring, mbarrier expect_tx, L2 evict_last on the
+//                        operand every tile re-reads
+//     warp 1 (1 thread)  MMA issuer: per K block 4 x 2 tcgen05.mma.cta_group::1.kind::f16 (M128 N192 K16) that
+//                        share one operand tile; tcgen05.commit frees the stage / publishes the accumulator
+//     warp 2             TMEM allocator: 512 columns = two 192-column fp32 accumulators (double buffered)
+//     warps 4..11        epilogue (two per TMEM lane quadrant): tcgen05.ld 32x32b.x32; K-chunk sums are promoted
+//                        into registers with IEEE round-to-nearest adds (the tensor core's own fp32 accumulation
+//                        truncates: measured -2.6e-5 relative bias over 782 K blocks without promotion)
+// Tile order: M tiles in groups of 11, M fastest inside a group (decode_tile) -- see DESIGN.md 4c.
+// Roofline: tensor pipe.  Executed flop per evaluation: 2 GEMMs x 2 products x 2*Mp*Np*Kp = 7.2e12 at N=50k,
+// L=200, q=21; measured 1.60-1.65 PFLOP/s per GEMM = 0.94-0.97 of the cuBLAS bf16 rate on the same part.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
