@@ -204,3 +204,69 @@ def test_shard_bounds():
             assert 0 <= lo <= hi <= n
             cover += list(range(lo, hi))
         assert cover == list(range(n))
+
+
+def test_ingest_property_random_alignments():
+    """hypothesis: for random A2M-like alignments (mixed case, '.', '-', invalid characters, wrapped lines) the
+    product ingest equals the oracle's per-character restatement of plmc's rules, in both gap modes."""
+    import tempfile
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    chars = "ACDEFGHIKLMNPQRSTVWY" + "acdefghiklmnpqrstvwy" + "--..XBZxb*"
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(2, 9), st.integers(4, 40), st.integers(0, 2 ** 31 - 1), st.booleans(), st.booleans())
+    def check(n_rows, width, seed, ignore_gaps, use_focus):
+        rng = np.random.default_rng(seed)
+        rows = ["".join(rng.choice(list(chars), width)) for _ in range(n_rows)]
+        # the focus row needs >= 2 upper-case residues to define model sites
+        f = list(rows[0])
+        f[0], f[width // 2] = "A", "W"
+        rows[0] = "".join(f)
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "r.a2m")
+            with open(p, "w") as fh:
+                for k, s in enumerate(rows):
+                    cut = int(rng.integers(1, width))
+                    fh.write(">%s/%d-%d some text\n%s\n%s\n" % ("q%d" % k, 7 + k, 7 + k + width, s[:cut], s[cut:]))
+            focus = "q0" if use_focus else None
+            ids, seqs = po.read_a2m(p)
+            try:
+                ref = po.prepare_alignment(ids, seqs, focus=focus, ignore_gaps=ignore_gaps)
+            except Exception:
+                ref = None
+            try:
+                ali = msa.load_alignment(p, focus=focus, ignore_gaps=ignore_gaps)
+            except msa.AlignmentError:
+                ali = None
+            if ref is None or ali is None:
+                # both must reject (e.g. fewer than two model sites)
+                assert ali is None and (ref is None or len(ref["focus_cols"]) < 2)
+                return
+            assert np.array_equal(ali.valid, ref["valid"])
+            assert np.array_equal(ali.codes, ref["codes"])
+            assert ali.q == ref["q"] and ali.gap_code == ref["gap_code"]
+            assert np.array_equal(ali.index_list, ref["index_list"])
+            assert ali.region_start == ref["region_start"] and ali.num_total_sites == ref["num_total_sites"]
+            if use_focus:
+                assert ali.target_seq == ref["target_seq"] and ali.focus_index == 0
+
+    check()
+
+
+def test_apc_and_frequency_normalisation_properties():
+    rng = np.random.default_rng(1)
+    for L, q in ((5, 21), (12, 20), (30, 5)):
+        Jt = rng.normal(0, 0.3, (L * (L - 1) // 2, q, q))
+        fn = np.sqrt((Jt ** 2).sum(axis=(1, 2)))
+        assert np.abs(model_io.apc_cn_scores(fn, L) - po.cn_scores(Jt, L)).max() < 1e-12
+        fi_c = rng.uniform(0, 5, (L, q))
+        fij_c = rng.uniform(0, 5, (L * (L - 1) // 2, q, q))
+        fi, fij = model_io.normalise_frequencies(fi_c, fij_c, 7.5, True)
+        assert np.allclose(fi.sum(axis=1), 1) and np.allclose(fij.sum(axis=(1, 2)), 1)
+        fi, fij = model_io.normalise_frequencies(fi_c, fij_c, 7.5, False)
+        assert np.allclose(fi, fi_c / 7.5) and np.allclose(fij, fij_c / 7.5)
+    # an all-gap column under ignore_gaps must not produce NaN
+    fi, fij = model_io.normalise_frequencies(np.zeros((3, 20)), np.zeros((3, 20, 20)), 1.0, True)
+    assert np.isfinite(fi).all() and np.isfinite(fij).all()
+    assert (model_io.apc_cn_scores(np.zeros(3), 3) == 0).all()
