@@ -64,3 +64,45 @@ def test_two_gpu_sharded_equals_single(tmp_path):
     prob.close()
     assert abs(float(d2["fx"]) - fx1) <= 1e-7 * abs(fx1)
     assert np.linalg.norm(d2["g"] - g1) <= 5e-6 * np.linalg.norm(g1)
+
+
+FIT_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from evcouplings_b200 import tools
+res, run = tools.run_plmc(sys.argv[1], sys.argv[2] + "_ECs.txt", sys.argv[2] + ".model", focus_seq="seq0", theta=0.8,
+                          iterations=25, lambda_h=0.01, lambda_J=7.8, return_run=True)
+np.save(sys.argv[2] + "_x_rank%%d.npy" %% dist.get_rank(), run.x)
+assert os.path.getsize(sys.argv[2] + ".model") > 0          # every rank returns after rank 0 wrote the files
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_two_gpu_full_fit_lockstep(tmp_path):
+    """run_plmc under a 2-rank NCCL group: sharded sequences, L-BFGS in lock-step, rank 0 writes the files;
+    parameters identical on both ranks and equal (fp32 noise) to the single-GPU fit."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from evcouplings_b200 import synthetic, tools
+    codes = synthetic.synthetic_msa_codes(400, 40, 17)
+    a2m = str(tmp_path / "a.a2m")
+    synthetic.write_a2m(a2m, codes)
+    script = tmp_path / "fit_worker.py"
+    script.write_text(FIT_WORKER)
+    prefix = str(tmp_path / "two")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", str(script), a2m, prefix]
+    subprocess.run(cmd, check=True, timeout=300)
+    x0, x1 = np.load(prefix + "_x_rank0.npy"), np.load(prefix + "_x_rank1.npy")
+    assert np.array_equal(x0, x1)
+    res, run = tools.run_plmc(a2m, str(tmp_path / "one_ECs.txt"), str(tmp_path / "one.model"), focus_seq="seq0",
+                              theta=0.8, iterations=25, lambda_h=0.01, lambda_J=7.8, return_run=True)
+    assert np.abs(run.x - x0).max() < 5e-3
+    two = np.loadtxt(prefix + "_ECs.txt", usecols=5)
+    one = np.loadtxt(str(tmp_path / "one_ECs.txt"), usecols=5)
+    assert np.sqrt(np.mean((two - one) ** 2)) < 1e-3
