@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libevcplm.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class EngineUnavailableError(RuntimeError):
@@ -26,6 +26,34 @@ c_void_p = ctypes.c_void_p
 c_i32 = ctypes.c_int32
 c_i64 = ctypes.c_int64
 c_f32 = ctypes.c_float
+c_f64 = ctypes.c_double
+
+
+class FitParams(ctypes.Structure):
+    """evc_fit_params_t (include/evcplm.h)."""
+    _fields_ = [("max_iterations", c_i32), ("m", c_i32), ("epsilon", c_f32), ("lambda_h", c_f32),
+                ("lambda_J", c_f32), ("max_linesearch", c_i32), ("min_step", c_f64), ("max_step", c_f64),
+                ("ftol", c_f64), ("gtol", c_f64), ("xtol", c_f64), ("precision_schedule", c_i32),
+                ("switch_factor", c_f32)]
+
+
+class FitResult(ctypes.Structure):
+    """evc_fit_result_t (include/evcplm.h)."""
+    _fields_ = [("status", c_i32), ("iterations", c_i32), ("evaluations", c_i32), ("switched_at", c_i32),
+                ("fx", c_f64), ("negloglk", c_f64), ("seconds", c_f64)]
+
+
+ALLREDUCE_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_i64, ctypes.c_void_p)
+PROGRESS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, c_i32, c_f64, c_f64, c_f64, c_f64, c_i32, c_f64,
+                               c_f64, c_f64)
+
+# status codes of evc_plm_fit -> libLBFGS names (what plmc prints after "Gradient optimization:")
+LBFGS_STATUS = {
+    0: "LBFGS_SUCCESS", 2: "LBFGS_ALREADY_MINIMIZED", -1021: "LBFGSERR_CANCELED",
+    -1000: "LBFGSERR_INVALIDPARAMETERS", -1001: "LBFGSERR_MINIMUMSTEP", -1002: "LBFGSERR_MAXIMUMSTEP",
+    -1003: "LBFGSERR_MAXIMUMLINESEARCH", -1004: "LBFGSERR_MAXIMUMITERATION", -1005: "LBFGSERR_WIDTHTOOSMALL",
+    -1006: "LBFGSERR_ROUNDING_ERROR", -1007: "LBFGSERR_INCREASEGRADIENT",
+}
 
 # name -> (restype, argtypes); mirrors include/evcplm.h one to one
 PROTOTYPES = {
@@ -38,12 +66,22 @@ PROTOTYPES = {
     "evc_hamming_num_tiles": (c_i64, [c_i64]),
     "evc_hamming_pack": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_void_p, c_void_p]),
     "evc_hamming_count_tiles": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_i32, c_i64, c_i64, c_void_p, c_void_p]),
+    "evc_a2m_scan": (ctypes.c_int, [ctypes.c_char_p, c_void_p, c_void_p, c_void_p]),
+    "evc_a2m_read": (ctypes.c_int, [ctypes.c_char_p, c_i64, c_i64, c_void_p, c_void_p, c_i64]),
+    "evc_msa_encode": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
+    "evc_identities_to_seq": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_void_p]),
     "evc_plm_create": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_i32]),
     "evc_plm_destroy": (None, [c_void_p]),
     "evc_plm_num_params": (c_i64, [c_void_p]),
     "evc_plm_eval_data": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "evc_plm_set_backward": (ctypes.c_int, [c_void_p, c_i32]),
     "evc_plm_set_forward": (ctypes.c_int, [c_void_p, c_i32]),
+    "evc_plm_set_precision": (ctypes.c_int, [c_void_p, c_i32]),
+    "evc_fit_default_params": (None, [c_void_p]),
+    "evc_plm_fit": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "evc_plm_pack_fx": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "evc_plm_unpack_fx": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "evc_plm_set_profiling": (ctypes.c_int, [c_void_p, c_i32]),
     "evc_plm_last_stage_ms": (ctypes.c_int, [c_void_p, c_void_p]),
     "evc_plm_add_regulariser": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32, c_void_p]),

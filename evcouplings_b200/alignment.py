@@ -8,6 +8,7 @@ reference functions they replace; the work runs in the kernels of libevcplm (no 
     num_cluster_members(matrix, identity_threshold)   <- alignment.py:1192-1233
     frequencies(matrix, seq_weights, num_symbols)     <- alignment.py:1078-1106
     pair_frequencies(matrix, seq_weights, num_symbols, fi)  <- alignment.py:1109-1153
+    identities_to_seq(seq, matrix)                    <- alignment.py:1156-1189
     set_weights(alignment, identity_threshold)        <- Alignment.set_weights :899-930 (duck-typed)
 """
 import numpy as np
@@ -38,9 +39,45 @@ def num_cluster_members(matrix, identity_threshold, engine=None):
     return eng.hamming_counts(m.astype(np.uint8), thr).astype(np.float64)
 
 
+def _as_codes(matrix, num_symbols):
+    """mapped integer matrix -> uint8 codes, range-checked BEFORE the narrowing cast (a symbol >= num_symbols
+    would index another site's coupling block inside the kernels)"""
+    m = np.ascontiguousarray(matrix)
+    if m.ndim != 2:
+        raise ValueError("matrix must be N x L")
+    if m.size and (m.min() < 0 or m.max() >= int(num_symbols)):
+        raise ValueError("mapped symbols must be in [0, %d)" % int(num_symbols))
+    return m.astype(np.uint8)
+
+
+def identities_to_seq(seq, matrix, engine=None):
+    """Number of identities of every sequence in ``matrix`` (N x L, mapped) to ``seq`` (length L, mapped).
+    Returns float64 of length N like the reference twin (alignment.py:1156-1189)."""
+    import ctypes
+    import torch
+    from . import _lib
+    eng = engine or _get_engine()
+    m = _as_codes(matrix, 256)
+    s = np.ascontiguousarray(seq)
+    N, L = m.shape
+    if s.shape != (L,):
+        raise ValueError("seq must have one entry per column of matrix")
+    if N == 0:
+        return np.zeros(0)
+    if s.min() < 0 or s.max() > 255:
+        raise ValueError("mapped symbols must be in [0, 256)")
+    d_m = torch.from_numpy(m).to(eng.device)
+    d_s = torch.from_numpy(s.astype(np.uint8)).to(eng.device)
+    out = torch.zeros(N, dtype=torch.int32, device=eng.device)
+    _lib.check(eng.lib.evc_identities_to_seq(eng.ptr(d_m), eng.ptr(d_s), N, L, eng.ptr(out), eng.stream()),
+               "evc_identities_to_seq")
+    eng.kernel_launches += 1
+    return out.cpu().numpy().astype(np.float64)
+
+
 def _problem(matrix, seq_weights, num_symbols, engine):
     eng = engine or _get_engine()
-    m = np.ascontiguousarray(matrix).astype(np.uint8)
+    m = _as_codes(matrix, num_symbols)
     w = np.ascontiguousarray(seq_weights, dtype=np.float32)
     return eng.plm_problem(m, w, int(num_symbols), -1, 0.0, 0.0, forward="gather", backward="gather")
 
@@ -79,6 +116,9 @@ def pair_frequencies(matrix, seq_weights, num_symbols, fi, engine=None):
 def set_weights(alignment, identity_threshold=0.8, engine=None):
     """Drop-in for ``Alignment.set_weights``: fills ``alignment.num_cluster_members`` and ``alignment.weights``
     (an object with ``matrix_mapped`` / ``__ensure_mapped_matrix`` semantics of the reference's Alignment)."""
+    ensure = getattr(alignment, "_Alignment__ensure_mapped_matrix", None)      # the reference's private helper
+    if ensure is not None:
+        ensure()
     mapped = getattr(alignment, "matrix_mapped", None)
     if mapped is None:
         from evcouplings.align.alignment import map_matrix
@@ -86,4 +126,7 @@ def set_weights(alignment, identity_threshold=0.8, engine=None):
         alignment.matrix_mapped = mapped
     alignment.num_cluster_members = num_cluster_members(mapped, identity_threshold, engine)
     alignment.weights = 1.0 / alignment.num_cluster_members
+    # like the reference (alignment.py:926-930): cached frequencies were computed with other / no weights
+    alignment._frequencies = None
+    alignment._pair_frequencies = None
     return alignment

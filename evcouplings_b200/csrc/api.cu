@@ -18,52 +18,6 @@ void set_error(const std::string &msg) { g_err = msg; }
 
 using namespace evc;
 
-struct evc_plm {
-    int device = 0;
-    PlmGeom g{};
-    uint8_t *d_codes = nullptr;     // [N][L] (kept for bucket building only; freed after create)
-    uint32_t *d_msa4 = nullptr;
-    uint32_t *d_perm = nullptr;
-    uint16_t *d_bstart = nullptr;
-    float *d_wts = nullptr;
-    float *d_W = nullptr;
-    float *d_G = nullptr;
-    float *d_R = nullptr;
-    float *d_gh_part = nullptr;
-    double *d_fx_part = nullptr;
-    float *d_x_tmp = nullptr;       // host-buffer convenience path
-    float *d_g_tmp = nullptr;
-    double *d_fx_tmp = nullptr;
-    // tensor-core backward (plm_tc.cu); allocated on first use
-    int bwd_mode = 0;               // 0 = gather/bucket kernel, 1 = tcgen05 GEMM
-    PlmTcGeom tc{};
-    void *d_xt = nullptr;
-    void *d_rt_hi = nullptr;
-    void *d_rt_lo = nullptr;
-    float *d_Gd = nullptr;
-    void *tc_maps = nullptr;        // host: 3 CUtensorMap
-    // tensor-core forward (plm_tc.cu); allocated on first use
-    int fwd_mode = 0;               // 0 = gather kernel, 1 = tcgen05 GEMM + softmax kernel
-    PlmTcfGeom tcf{};
-    void *d_x1h = nullptr;
-    void *d_wt_hi = nullptr;
-    void *d_wt_lo = nullptr;
-    float *d_zt = nullptr;
-    float *d_gh_part2 = nullptr;
-    double *d_fx_part2 = nullptr;
-    void *tcf_maps = nullptr;
-    // fused tensor-core forward (softmax epilogue on the accumulator)
-    PlmTcffGeom tcff{};
-    void *d_wp_hi = nullptr;
-    void *d_wp_lo = nullptr;
-    float *d_gh_part3 = nullptr;
-    double *d_fx_part3 = nullptr;
-    void *tcff_maps = nullptr;
-    bool profiling = false;         // record CUDA events around the stages of evc_plm_eval_data
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false;
-};
-
 static cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 extern "C" {
@@ -150,6 +104,13 @@ int evc_hamming_counts(const uint8_t *codes, int64_t N, int32_t L, int32_t min_i
     return rc;
 }
 
+int evc_identities_to_seq(const uint8_t *d_codes, const uint8_t *d_seq, int64_t N, int32_t L, int32_t *d_out,
+                          void *stream)
+{
+    if (!d_codes || !d_seq || !d_out) { set_error("evc_identities_to_seq: null pointer"); return 1; }
+    return identities_to_seq(d_codes, d_seq, N, L, d_out, as_stream(stream));
+}
+
 // ---- (a) PLM ---------------------------------------------------------------------------------------
 void evc_plm_destroy(evc_plm_t *h)
 {
@@ -187,6 +148,7 @@ void evc_plm_destroy(evc_plm_t *h)
     free(h->tcff_maps);
     for (int k = 0; k < 6; k++)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    fit_work_free(h->fit);
     delete h;
 }
 
@@ -206,6 +168,18 @@ int evc_plm_create(evc_plm_t **out, const uint8_t *codes, int64_t N, int32_t L, 
         return 1;
     }
     if (L > 65535) { set_error("evc_plm_create: L too large"); return 1; }
+    // every code must address a row of a coupling block: 0..q-1, or q for the ignored gap (the kernels index
+    // shared-memory rows with the raw byte, so an out-of-range code would silently read another site's block)
+    {
+        unsigned mx = 0;
+        const size_t total = (size_t)N * L;
+        for (size_t e = 0; e < total; e++) mx = codes[e] > mx ? codes[e] : mx;
+        if ((int)mx >= (gap_code >= 0 ? q + 1 : q)) {
+            set_error("evc_plm_create: sequence code " + std::to_string(mx) + " out of range (valid: 0.." +
+                      std::to_string((gap_code >= 0 ? q + 1 : q) - 1) + (gap_code >= 0 ? ", the last one being the ignored gap)" : ")"));
+            return 1;
+        }
+    }
     EVC_CUDA(cudaSetDevice(device));
     evc_plm *h = new (std::nothrow) evc_plm();
     if (!h) { set_error("evc_plm_create: out of host memory"); return 1; }
@@ -225,16 +199,9 @@ int evc_plm_create(evc_plm_t **out, const uint8_t *codes, int64_t N, int32_t L, 
     g.ntiles_b = (int)ceil_div(N, PLM_BWD_TS);
     g.n_params = (int64_t)L * q + (int64_t)L * (L - 1) / 2 * q * q;
 
-    const size_t w_bytes = (size_t)g.w_floats() * sizeof(float);
     bool ok = cudaMalloc(&h->d_codes, (size_t)N * L) == cudaSuccess &&
               cudaMalloc(&h->d_msa4, (size_t)g.L4 * g.Nld * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMalloc(&h->d_perm, (size_t)g.ntiles_b * L * PLM_BWD_CAP * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMalloc(&h->d_bstart, (size_t)g.ntiles_b * L * PLM_BWD_BS * sizeof(uint16_t)) == cudaSuccess &&
-              cudaMalloc(&h->d_wts, (size_t)N * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&h->d_W, w_bytes) == cudaSuccess && cudaMalloc(&h->d_G, w_bytes) == cudaSuccess &&
-              cudaMalloc(&h->d_R, (size_t)L * g.Nr * g.S * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&h->d_gh_part, (size_t)L * g.ntiles_f * g.S * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&h->d_fx_part, (size_t)L * g.ntiles_f * sizeof(double)) == cudaSuccess;
+              cudaMalloc(&h->d_wts, (size_t)N * sizeof(float)) == cudaSuccess;
     if (!ok) {
         set_error(std::string("evc_plm_create: device allocation failed: ") +
                   cudaGetErrorString(cudaGetLastError()));
@@ -242,23 +209,57 @@ int evc_plm_create(evc_plm_t **out, const uint8_t *codes, int64_t N, int32_t L, 
         return 1;
     }
     ok = cudaMemcpy(h->d_codes, codes, (size_t)N * L, cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemcpy(h->d_wts, weights, (size_t)N * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemset(h->d_W, 0, w_bytes) == cudaSuccess &&
-         cudaMemset(h->d_R, 0, (size_t)L * g.Nr * g.S * sizeof(float)) == cudaSuccess;
-    if (!ok || plm_pack_msa(g, h->d_codes, h->d_msa4, 0) || plm_build_buckets(g, h->d_codes, h->d_perm, h->d_bstart, 0) ||
-        cudaDeviceSynchronize() != cudaSuccess) {
+         cudaMemcpy(h->d_wts, weights, (size_t)N * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok || plm_pack_msa(g, h->d_codes, h->d_msa4, 0) || cudaDeviceSynchronize() != cudaSuccess) {
         if (ok) set_error(std::string("evc_plm_create: packing failed: ") + cudaGetErrorString(cudaGetLastError()));
         else set_error("evc_plm_create: H2D failed");
         evc_plm_destroy(h);
         return 1;
     }
-    cudaFree(h->d_codes);
-    h->d_codes = nullptr;
     *out = h;
     return 0;
 }
 
+// Buffers of the gather path (expanded couplings W, their gradient G, residuals R, state-sorted bucket lists):
+// 6.7 GB of R alone at N = 100k, L = 800 -- allocated only when a gather kernel is actually selected.
+static int ensure_gather(evc_plm *h)
+{
+    if (h->gather_ready) return 0;
+    EVC_CUDA(cudaSetDevice(h->device));
+    const PlmGeom &g = h->g;
+    const size_t w_bytes = (size_t)g.w_floats() * sizeof(float);
+    const size_t r_bytes = (size_t)g.L * g.Nr * g.S * sizeof(float);
+    const bool ok = cudaMalloc(&h->d_perm, (size_t)g.ntiles_b * g.L * PLM_BWD_CAP * sizeof(uint32_t)) == cudaSuccess &&
+                    cudaMalloc(&h->d_bstart, (size_t)g.ntiles_b * g.L * PLM_BWD_BS * sizeof(uint16_t)) == cudaSuccess &&
+                    cudaMalloc(&h->d_W, w_bytes) == cudaSuccess && cudaMalloc(&h->d_G, w_bytes) == cudaSuccess &&
+                    cudaMalloc(&h->d_R, r_bytes) == cudaSuccess &&
+                    cudaMalloc(&h->d_gh_part, (size_t)g.L * g.ntiles_f * g.S * sizeof(float)) == cudaSuccess &&
+                    cudaMalloc(&h->d_fx_part, (size_t)g.L * g.ntiles_f * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+        set_error(std::string("libevcplm: device allocation of the gather-path buffers failed: ") +
+                  cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    EVC_CUDA(cudaMemset(h->d_W, 0, w_bytes));
+    EVC_CUDA(cudaMemset(h->d_R, 0, r_bytes));
+    if (plm_build_buckets(g, h->d_codes, h->d_perm, h->d_bstart, 0)) return 1;
+    EVC_CUDA(cudaDeviceSynchronize());
+    h->gather_ready = true;
+    return 0;
+}
+
 int64_t evc_plm_num_params(const evc_plm_t *h) { return h ? h->g.n_params : -1; }
+
+int evc_plm_set_precision(evc_plm_t *h, int32_t mode)
+{
+    if (!h) { set_error("evc_plm_set_precision: null handle"); return 1; }
+    if (mode != 0 && mode != 1) {
+        set_error("evc_plm_set_precision: mode must be 0 (fp32-equivalent, bf16 hi+lo products) or 1 (bf16 tiles)");
+        return 1;
+    }
+    h->precision = mode;
+    return 0;
+}
 
 int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, void *stream)
 {
@@ -269,34 +270,37 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
     const bool tc = h->bwd_mode == 1;
     const bool tcf = h->fwd_mode == 1;
     const bool tcff = h->fwd_mode == 2;
+    const int single = h->precision == 1 ? 1 : 0;      // only the tensor-core products have a reduced mode
+    void *rt_lo = single ? nullptr : h->d_rt_lo;
     float *gJ = d_g + (int64_t)g.L * g.q;
+    if ((!tc || (!tcf && !tcff)) && ensure_gather(h)) return 1;
     if (prof) EVC_CUDA(cudaEventRecord(h->ev[0], st));
     if (tcff) {
         // expand -> fused tcgen05 forward (logits + softmax + residuals) -> tcgen05 backward GEMM
-        if (plm_tcff_expand(g, h->tcff, d_x, h->d_wp_hi, h->d_wp_lo, st)) return 1;
+        if (plm_tcff_expand(g, h->tcff, d_x, h->d_wp_hi, h->d_wp_lo, single, st)) return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
         if (plm_tcff_forward(g, h->tcff, h->tcff_maps, d_x, h->d_msa4, h->d_wts, h->d_rt_hi, h->d_rt_lo, h->tc.Kp,
-                             h->d_gh_part3, h->d_fx_part3, st))
+                             h->d_gh_part3, h->d_fx_part3, single, st))
             return 1;
         if (prof) {
             EVC_CUDA(cudaEventRecord(h->ev[2], st));
             EVC_CUDA(cudaEventRecord(h->ev[3], st));
         }
-        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, single, st)) return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
         if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, gJ, 1.0f, st)) return 1;
         if (plm_finalize_fields_n(g, h->d_gh_part3, h->d_fx_part3, d_g, d_fx, h->tcff.ntile_part, st)) return 1;
     } else if (tcf) {
         // expand -> tcgen05 logits GEMM -> softmax/residuals -> tcgen05 backward GEMM
-        if (plm_tcf_expand(g, h->tcf, d_x, h->d_wt_hi, h->d_wt_lo, st)) return 1;
+        if (plm_tcf_expand(g, h->tcf, d_x, h->d_wt_hi, h->d_wt_lo, single, st)) return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[1], st));
-        if (plm_tcf_logits(g, h->tcf, h->tcf_maps, h->d_zt, st)) return 1;
+        if (plm_tcf_logits(g, h->tcf, h->tcf_maps, h->d_zt, single, st)) return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[2], st));
-        if (plm_tcf_softmax(g, h->tcf, h->d_zt, d_x, h->d_msa4, h->d_wts, h->d_rt_hi, h->d_rt_lo, h->tc.Kp,
+        if (plm_tcf_softmax(g, h->tcf, h->d_zt, d_x, h->d_msa4, h->d_wts, h->d_rt_hi, rt_lo, h->tc.Kp,
                             h->d_gh_part2, h->d_fx_part2, st))
             return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[3], st));
-        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, single, st)) return 1;
         if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
         if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, gJ, 1.0f, st)) return 1;
         if (plm_finalize_fields_n(g, h->d_gh_part2, h->d_fx_part2, d_g, d_fx, h->tcf.ntiles_s, st)) return 1;
@@ -312,7 +316,7 @@ int evc_plm_eval_data(evc_plm_t *h, const float *d_x, float *d_g, double *d_fx, 
             EVC_CUDA(cudaEventRecord(h->ev[3], st));
         }
         if (tc) {
-            if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, st)) return 1;
+            if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, single, st)) return 1;
             if (prof) EVC_CUDA(cudaEventRecord(h->ev[4], st));
             if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, gJ, 1.0f, st)) return 1;
             if (plm_finalize_fields(g, h->d_gh_part, h->d_fx_part, d_g, d_fx, st)) return 1;
@@ -474,6 +478,17 @@ int evc_plm_weighted_counts(evc_plm_t *h, float *d_fi_counts, float *d_fij_count
     if (!h || !d_fi_counts || !d_fij_counts) { set_error("evc_plm_weighted_counts: null pointer"); return 1; }
     cudaStream_t st = as_stream(stream);
     const PlmGeom &g = h->g;
+    if (h->bwd_mode == 1 && h->d_gh_part2) {
+        // tensor-core path: f_ij = Xt (w X)^T through the same backward product (weights as bf16 hi + lo)
+        const int ntiles = h->tcf.ntiles_s;
+        if (plm_tc_onehot_residual(g, ntiles, h->d_msa4, h->d_wts, h->d_rt_hi, h->d_rt_lo, h->tc.Kp, h->d_gh_part2,
+                                   h->d_fx_part2, st))
+            return 1;
+        if (plm_tc_backward(g, h->tc, h->tc_maps, h->d_Gd, 0, st)) return 1;
+        if (plm_tc_finalize_pairs(g, h->tc, h->d_Gd, d_fij_counts, 0.5f, st)) return 1;
+        return plm_finalize_fields_n(g, h->d_gh_part2, nullptr, d_fi_counts, nullptr, ntiles, st);
+    }
+    if (ensure_gather(h)) return 1;
     EVC_CUDA(cudaMemsetAsync(h->d_G, 0, (size_t)g.w_floats() * sizeof(float), st));
     if (plm_onehot_residual(g, h->d_msa4, h->d_wts, h->d_R, h->d_gh_part, st)) return 1;
     if (plm_backward(g, h->d_R, h->d_perm, h->d_bstart, h->d_G, st)) return 1;
@@ -493,6 +508,7 @@ int evc_plm_energies(evc_plm_t *h, const float *d_x, double *d_out, void *stream
     if (!h || !d_x || !d_out) { set_error("evc_plm_energies: null pointer"); return 1; }
     cudaStream_t st = as_stream(stream);
     const PlmGeom &g = h->g;
+    if (ensure_gather(h)) return 1;
     if (plm_expand(g, d_x, h->d_W, st)) return 1;
     // the residual buffer (L * Nr * S floats) is free outside an evaluation: reuse it for the per-site partials
     return plm_energies(g, h->d_W, d_x, h->d_msa4, h->d_R, d_out, st);

@@ -64,6 +64,11 @@ __device__ __forceinline__ void tile_from_index(int64_t idx, int64_t T, int64_t 
     C = r + (idx - (r * T - r * (r - 1) / 2));
 }
 
+// Column owned by counter c of thread tx: {4 tx .. 4 tx + 3} and {64 + 4 tx .. 64 + 4 tx + 3}.  A quarter warp then
+// reads 8 x 16 contiguous bytes of s_col per 128-bit load (conflict-free); the round-1 mapping 8 tx + c put
+// threads tx and tx + 4 on the same banks (2-way conflicts on 31 % of the wavefronts, profiles/r1_ncu_full_hamming_final.csv).
+__device__ __forceinline__ int hcol(int tx, int c) { return (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4); }
+
 // FILTER = false: full comparison, neighbour counts credited directly (with exact early termination).
 // FILTER = true : phase 1 of the two-phase scheme -- only the first W1 plane words are compared; a pair whose
 //                 identities so far plus everything it could still gain reach the threshold is appended to a
@@ -123,8 +128,8 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
             for (int p = 0; p < HP; p++) {
                 const uint4 a0 = *reinterpret_cast<const uint4 *>(&s_row[ww][p][ty * 8]);
                 const uint4 a1 = *reinterpret_cast<const uint4 *>(&s_row[ww][p][ty * 8 + 4]);
-                const uint4 b0 = *reinterpret_cast<const uint4 *>(&s_col[ww][p][tx * 8]);
-                const uint4 b1 = *reinterpret_cast<const uint4 *>(&s_col[ww][p][tx * 8 + 4]);
+                const uint4 b0 = *reinterpret_cast<const uint4 *>(&s_col[ww][p][tx * 4]);
+                const uint4 b1 = *reinterpret_cast<const uint4 *>(&s_col[ww][p][64 + tx * 4]);
                 a[p][0] = a0.x; a[p][1] = a0.y; a[p][2] = a0.z; a[p][3] = a0.w;
                 a[p][4] = a1.x; a[p][5] = a1.y; a[p][6] = a1.z; a[p][7] = a1.w;
                 b[p][0] = b0.x; b[p][1] = b0.y; b[p][2] = b0.z; b[p][3] = b0.w;
@@ -140,7 +145,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
                     cnt[r][c] += __popc(~d);
                 }
             const int wdone = w0 + ww;
-            if (!FILTER && wdone >= 1 && wdone + 1 < W) {
+            if (!FILTER && W1 >= 0 && wdone >= 1 && wdone + 1 < W) {      // W1 < 0: early termination disabled (bench hook)
                 const int need = thr - 32 * (W - 1 - wdone);
                 int alive = 0;
 #pragma unroll
@@ -162,7 +167,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
         for (int r = 0; r < 8; r++)
 #pragma unroll
             for (int c = 0; c < 8; c++)
-                mine += (row0 + ty * 8 + r < N && col0 + tx * 8 + c < N && cnt[r][c] >= need) ? 1 : 0;
+                mine += (row0 + ty * 8 + r < N && col0 + hcol(tx, c) < N && cnt[r][c] >= need) ? 1 : 0;
         const int lane = tid & 31;
         int incl = mine;
 #pragma unroll
@@ -180,7 +185,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
         for (int r = 0; r < 8; r++)
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-                const int64_t gr = row0 + ty * 8 + r, gc = col0 + tx * 8 + c;
+                const int64_t gr = row0 + ty * 8 + r, gc = col0 + hcol(tx, c);
                 if (gr < N && gc < N && cnt[r][c] >= need) {
                     if (slot < cand_cap)
                         cand[slot] = make_uint2((unsigned)gr, (unsigned)gc | (diag ? 0u : 0x80000000u));
@@ -199,7 +204,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
     for (int r = 0; r < 8; r++)
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const bool ok = (row0 + ty * 8 + r < N) && (col0 + tx * 8 + c < N);
+            const bool ok = (row0 + ty * 8 + r < N) && (col0 + hcol(tx, c) < N);
             const int f = (ok && cnt[r][c] >= thr) ? 1 : 0;
             rs[r] += f;
             cs[c] += f;
@@ -210,7 +215,7 @@ hamming_tile_kernel(const uint32_t *__restrict__ planes, int64_t N, int W, int t
     if (!diag) {
 #pragma unroll
         for (int c = 0; c < 8; c++)
-            if (cs[c]) atomicAdd(&s_csum[tx * 8 + c], cs[c]);
+            if (cs[c]) atomicAdd(&s_csum[hcol(tx, c)], cs[c]);
     }
     __syncthreads();
     if (tid < HT) {
@@ -247,6 +252,17 @@ __global__ void hamming_verify_kernel(const uint32_t *__restrict__ planes, int64
     }
 }
 
+// test / bench hooks, read once per process (tests drive them from subprocesses)
+static long long env_once(const char *name, long long *cache)
+{
+    if (*cache == -2) {
+        const char *e = getenv(name);
+        *cache = e ? atoll(e) : -1;
+    }
+    return *cache;
+}
+static long long g_env_cap = -2, g_env_single = -2, g_env_noprune = -2;
+
 struct HammingScratch {
     uint2 *cand = nullptr;
     unsigned long long *count = nullptr;
@@ -263,7 +279,7 @@ static int hamming_scratch(unsigned long long want, HammingScratch **out)
         set_error("hamming: scratch allocation failed");
         return 1;
     }
-    if (h.cap < want || getenv("EVC_HAMMING_CAND_CAP") != nullptr) {
+    if (h.cap != want && (h.cap < want || env_once("EVC_HAMMING_CAND_CAP", &g_env_cap) > 0)) {
         cudaFree(h.cand);
         h.cand = nullptr;
         h.cap = 0;
@@ -275,6 +291,30 @@ static int hamming_scratch(unsigned long long want, HammingScratch **out)
         h.cap = want;
     }
     *out = &h;
+    return 0;
+}
+
+// f3: identities of every sequence to one target sequence (reference twin evcouplings/align/alignment.py:1156-1189):
+// warp = sequence, lanes stride over the sites (coalesced 32-byte segments), shuffle reduction.  HBM-streaming.
+__global__ void identities_to_seq_kernel(const uint8_t *__restrict__ codes, const uint8_t *__restrict__ seq, int64_t N,
+                                         int L, int *__restrict__ out)
+{
+    const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint8_t *row = codes + n * L;
+    int acc = 0;
+    for (int j = lane; j < L; j += 32) acc += (row[j] == seq[j]) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[n] = acc;
+}
+
+int identities_to_seq(const uint8_t *d_codes, const uint8_t *d_seq, int64_t N, int L, int *d_out, cudaStream_t st)
+{
+    if (N <= 0 || L <= 0) { set_error("identities_to_seq: empty alignment"); return 1; }
+    identities_to_seq_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(d_codes, d_seq, N, L, d_out);
+    EVC_KERNEL_CHECK();
     return 0;
 }
 
@@ -316,11 +356,13 @@ int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_iden
     // The filter only pays when it can reject: the identities still obtainable after W1 words, 32 * (W - W1),
     // must be well below the threshold.  Falls back to the single-phase kernel if the candidate list overflows.
     const int W1 = (W * 3 + 9) / 10;
-    const bool two_phase = W >= 6 && (thr - 32 * (W - W1)) >= 8 && getenv("EVC_HAMMING_SINGLE_PHASE") == nullptr;
+    const bool no_prune = env_once("EVC_HAMMING_NO_PRUNE", &g_env_noprune) > 0;    // bench: un-pruned reference time
+    const bool two_phase = W >= 6 && (thr - 32 * (W - W1)) >= 8 && !no_prune &&
+                           env_once("EVC_HAMMING_SINGLE_PHASE", &g_env_single) <= 0;
     if (two_phase) {
         HammingScratch *hs = nullptr;
         unsigned long long want = (unsigned long long)std::min<int64_t>((int64_t)1 << 27, std::max<int64_t>(N * 512, 1 << 20));
-        if (const char *e = getenv("EVC_HAMMING_CAND_CAP")) want = (unsigned long long)std::max(1ll, atoll(e));   // tests
+        if (env_once("EVC_HAMMING_CAND_CAP", &g_env_cap) > 0) want = (unsigned long long)g_env_cap;   // tests
         if (hamming_scratch(want, &hs) == 0) {
             EVC_CUDA(cudaMemsetAsync(hs->count, 0, sizeof(unsigned long long), st));
             int64_t done = tile_begin;
@@ -348,8 +390,8 @@ int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_iden
     int64_t done = tile_begin;
     while (done < tile_end) {                        // grid.x limit 2^31-1
         const int64_t nblk = std::min<int64_t>(tile_end - done, (int64_t)1 << 30);
-        hamming_tile_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts, W, nullptr,
-                                                                      nullptr, 0);
+        hamming_tile_kernel<false><<<(unsigned)nblk, 256, smem, st>>>(d_planes, N, W, thr, done, T, d_counts,
+                                                                      no_prune ? -1 : W, nullptr, nullptr, 0);
         EVC_KERNEL_CHECK();
         done += nblk;
     }

@@ -12,6 +12,8 @@ int hamming_pack(const uint8_t *d_codes, int64_t N, int L, uint32_t *d_planes, c
 int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_identical,
                         int64_t tile_begin, int64_t tile_end, int *d_counts, cudaStream_t st);
 
+int identities_to_seq(const uint8_t *d_codes, const uint8_t *d_seq, int64_t N, int L, int *d_out, cudaStream_t st);
+
 // plm_gather.cu -- geometry of the expanded coupling tensor and the gather-path kernels
 struct PlmGeom {
     int64_t N;        // sequences on this handle
@@ -64,7 +66,10 @@ void plm_tc_geometry(const PlmGeom &g, PlmTcGeom &t);
 size_t plm_tc_map_bytes();
 int plm_tc_build_xt(const PlmGeom &g, const PlmTcGeom &t, const uint32_t *d_msa4, void *d_xt, cudaStream_t st);
 int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_lo, void *maps_out_host);
-int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps_host, float *d_Gd, cudaStream_t st);
+int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps_host, float *d_Gd, int single,
+                    cudaStream_t st);
+int plm_tc_onehot_residual(const PlmGeom &g, int ntiles, const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi,
+                           void *d_rt_lo, int64_t Kp, float *d_gh_part, double *d_fx_part, cudaStream_t st);
 int plm_tc_finalize_pairs(const PlmGeom &g, const PlmTcGeom &t, const float *d_Gd, float *d_gJ, float scale,
                           cudaStream_t st);
 // tensor-core forward: Zt = (Wt_hi + Wt_lo) X^T on tcgen05, then softmax/residual kernel
@@ -79,8 +84,9 @@ void plm_tcf_geometry(const PlmGeom &g, PlmTcfGeom &t);
 int plm_tcf_build_x(const PlmGeom &g, const PlmTcfGeom &t, const uint32_t *d_msa4, void *d_x1h, cudaStream_t st);
 int plm_tcf_make_maps(const PlmTcfGeom &t, void *d_wt_hi, void *d_wt_lo, void *d_x1h, void *maps_out_host);
 int plm_tcf_expand(const PlmGeom &g, const PlmTcfGeom &t, const float *d_x, void *d_wt_hi, void *d_wt_lo,
+                   int single, cudaStream_t st);
+int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps_host, float *d_zt, int single,
                    cudaStream_t st);
-int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps_host, float *d_zt, cudaStream_t st);
 int plm_tcf_softmax(const PlmGeom &g, const PlmTcfGeom &t, const float *d_zt, const float *d_x,
                     const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
                     float *d_gh_part, double *d_fx_part, cudaStream_t st);
@@ -97,10 +103,10 @@ void plm_tcff_geometry(const PlmGeom &g, PlmTcffGeom &t);
 bool plm_tcff_supported(const PlmGeom &g);
 int plm_tcff_make_maps(const PlmTcffGeom &t, void *d_x1h, void *d_wp_hi, void *d_wp_lo, void *maps_out_host);
 int plm_tcff_expand(const PlmGeom &g, const PlmTcffGeom &t, const float *d_x, void *d_wp_hi, void *d_wp_lo,
-                    cudaStream_t st);
+                    int single, cudaStream_t st);
 int plm_tcff_forward(const PlmGeom &g, const PlmTcffGeom &t, const void *maps_host, const float *d_x,
                      const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
-                     float *d_gh_part, double *d_fx_part, cudaStream_t st);
+                     float *d_gh_part, double *d_fx_part, int single, cudaStream_t st);
 int plm_finalize_fields_n(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                           double *d_fx, int ntiles, cudaStream_t st);
 int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
@@ -122,4 +128,60 @@ int lbfgs_update_pair(float *s, float *y, const float *x, const float *xp, const
                       const float *gp, double *ys, double *yy, int64_t n, cudaStream_t st);
 int fn_scores(const float *J, int L, int q, float *fn, cudaStream_t st);
 
+// fit.cu
+struct FitWork;
+void fit_work_free(FitWork *w);
+
 }  // namespace evc
+
+// The handle behind evc_plm_t (include/evcplm.h).  Defined here because api.cu (objective) and fit.cu (L-BFGS
+// driver) both work on it.
+struct evc_plm {
+    int device = 0;
+    evc::PlmGeom g{};
+    uint8_t *d_codes = nullptr;     // [N][L] (kept: the gather path's bucket lists are built lazily from it)
+    uint32_t *d_msa4 = nullptr;
+    float *d_wts = nullptr;
+    // gather path (plm_gather.cu): allocated on first use (ensure_gather) -- the tensor-core path never needs it
+    bool gather_ready = false;
+    uint32_t *d_perm = nullptr;
+    uint16_t *d_bstart = nullptr;
+    float *d_W = nullptr;
+    float *d_G = nullptr;
+    float *d_R = nullptr;
+    float *d_gh_part = nullptr;
+    double *d_fx_part = nullptr;
+    float *d_x_tmp = nullptr;       // host-buffer convenience path
+    float *d_g_tmp = nullptr;
+    double *d_fx_tmp = nullptr;
+    int precision = 0;              // 0 = fp32-equivalent (bf16 hi + lo products), 1 = bf16 tiles (one product)
+    // tensor-core backward (plm_tc.cu); allocated on first use
+    int bwd_mode = 0;               // 0 = gather/bucket kernel, 1 = tcgen05 GEMM
+    evc::PlmTcGeom tc{};
+    void *d_xt = nullptr;
+    void *d_rt_hi = nullptr;
+    void *d_rt_lo = nullptr;
+    float *d_Gd = nullptr;
+    void *tc_maps = nullptr;        // host: 3 CUtensorMap
+    // tensor-core forward (plm_tc.cu); allocated on first use
+    int fwd_mode = 0;               // 0 = gather kernel, 1 = tcgen05 GEMM + softmax kernel, 2 = fused epilogue
+    evc::PlmTcfGeom tcf{};
+    void *d_x1h = nullptr;
+    void *d_wt_hi = nullptr;
+    void *d_wt_lo = nullptr;
+    float *d_zt = nullptr;
+    float *d_gh_part2 = nullptr;
+    double *d_fx_part2 = nullptr;
+    void *tcf_maps = nullptr;
+    // fused tensor-core forward (softmax epilogue on the accumulator)
+    evc::PlmTcffGeom tcff{};
+    void *d_wp_hi = nullptr;
+    void *d_wp_lo = nullptr;
+    float *d_gh_part3 = nullptr;
+    double *d_fx_part3 = nullptr;
+    void *tcff_maps = nullptr;
+    bool profiling = false;         // record CUDA events around the stages of evc_plm_eval_data
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    evc::FitWork *fit = nullptr;    // L-BFGS workspace (fit.cu), allocated by the first evc_plm_fit
+};

@@ -43,11 +43,11 @@ namespace evc {
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 192;
 constexpr int TC_BK = 64;
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 8;   // ring depth is chosen at launch from the stage size (hi+lo: 3-4, bf16x1: 5)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16384
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;        // 24576
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;   // 65536
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_SMEM_LIMIT = 232448;                // 227 KB opt-in shared memory per CTA
+constexpr int TC_SMEM_HEAD = 2048;                   // 1 KB alignment slack + 1 KB of mbarriers / TMEM slot
 constexpr int TC_THREADS = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: epilogue (2 per TMEM lane quadrant)
 constexpr int TC_K_CHUNK = 32;   // k-blocks (of 64) accumulated in TMEM before promotion to an fp32 add
 
@@ -119,23 +119,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// A operand from tensor memory (TS form): the shared operand of the hi/lo MMA pair is copied smem -> TMEM once
-// (tcgen05.cp, 128 lanes x 256 bit = one K=16 slice) and both MMAs read it from there, which removes ~45 % of
-// the shared-memory operand traffic that bounds the SS form at M128 x N<=192.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate)
-{
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc)
-{
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -162,226 +145,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Persistent variant with a double-buffered TMEM accumulator (2 x 192 columns): the epilogue of tile t
-// overlaps the main loop of tile t+1.  Used for the FORWARD product, which has many short tiles:
-//     Zt[(i,a), n] = sum_(j,b) (Wt_hi + Wt_lo)[(i,a),(j,b)] * X[n,(j,b)]
-// SPLIT_A = 1: operands (A_hi, A_lo, B), two MMAs share B;  SPLIT_A = 0: (A, B_hi, B_lo), two MMAs share A.
-// Tiles are enumerated with the M index fastest so that concurrently running CTAs share the B tile.
+// tcgen05.ld wrappers (32 lanes x 32 bit, N consecutive columns per thread)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Tile enumeration: M tiles are swept in groups of `mgroup`; inside a group the M index is fastest, then the N
-// tile.  For the forward product (SPLIT_A) a group of 11 M tiles = 24 MB of the coupling operand stays L2
-// resident while every sequence tile passes by (the whole 71 MB operand does not: the 126 MB L2 is two
-// partitions); the backward uses one group (all CTAs advance along K together and share operand tiles in time).
-__device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, int mgroup, int &m_tile, int &n_tile)
-{
-    const int full = (m_tiles / mgroup) * mgroup * n_tiles;
-    if (tile < full) {
-        const int per = mgroup * n_tiles;
-        const int g = tile / per, r = tile - g * per;
-        n_tile = r / mgroup;
-        m_tile = g * mgroup + (r - n_tile * mgroup);
-    } else {
-        const int rem = m_tiles % mgroup, r = tile - full;
-        n_tile = r / rem;
-        m_tile = (m_tiles / mgroup) * mgroup + (r - n_tile * rem);
-    }
-}
-
-template <int SPLIT_A>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                          const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
-                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int a_tmem, int mgroup)
-{
-    // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
-    // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
-    // 782 k-blocks); accumulating at most k_chunk k-blocks in TMEM and adding the chunk results in the
-    // epilogue (IEEE round-to-nearest) keeps it at the level of a plain fp32 sum.
-    constexpr int BYTES0 = SPLIT_A ? TC_A_BYTES : TC_A_BYTES;       // operand 0: A or A_hi (128 rows)
-    constexpr int BYTES1 = SPLIT_A ? TC_A_BYTES : TC_B_BYTES;       // operand 1: A_lo or B_hi
-    constexpr int BYTES2 = TC_B_BYTES;                              // operand 2: B or B_lo (192 rows)
-    constexpr int STAGE = BYTES0 + BYTES1 + BYTES2;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
-                                                            ~static_cast<uintptr_t>(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE);
-    uint64_t *empty = full + TC_STAGES;
-    uint64_t *acc_full = empty + TC_STAGES;      // [2]
-    uint64_t *acc_empty = acc_full + 2;          // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = m_tiles * n_tiles;
-    const int n_chunks = (num_kb + k_chunk - 1) / k_chunk;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        for (int a = 0; a < 2; a++) {
-            mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 8);         // one arrival per epilogue warp
-        }
-        mbar_fence_init();
-    }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
-        // SPLIT_A (forward): the coupling matrix (A_hi, A_lo; 71 MB) is re-read by every sequence tile -> evict_last
-        const uint64_t keep = l2_policy_evict_last();
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int m_tile, n_tile;
-            decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
-            for (int kb = 0; kb < num_kb; kb++, it++) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-                mbar_wait_bounded(&empty[s], ph ^ 1u);
-                unsigned char *st = smem + s * STAGE;
-                mbar_expect_tx(&full[s], STAGE);
-                if (SPLIT_A) {
-                    tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
-                    tma_load_2d_hint(st + BYTES0, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
-                } else {
-                    tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
-                    tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
-                }
-                tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
-            }
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
-        int it = 0, wl = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int c = 0; c < n_chunks; c++, wl++) {
-                const int acc = wl & 1;
-                mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((wl >> 1) & 1) ^ 1));
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
-                const int kb0 = c * k_chunk, kb1 = min(num_kb, kb0 + k_chunk);
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const int s = it % TC_STAGES;
-                    const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-                    mbar_wait_bounded(&full[s], ph);
-                    tc_fence_after();
-                    unsigned char *st = smem + s * STAGE;
-                    const uint64_t d0 = make_desc_sw128(st);
-                    const uint64_t d1 = make_desc_sw128(st + BYTES0);
-                    const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
-                    if (!SPLIT_A && a_tmem) {
-                        // stage the shared A tile of this k-block in TMEM (columns 384 + 32*s ..), 8 columns per K=16
-                        const uint32_t ta = tmem_base + 2u * TC_BN + (uint32_t)(s * 32);
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 16; k++)
-                            tmem_cp_128x256b(ta + (uint32_t)(k * 8), d0 + (uint64_t)((k * 16 * 2) >> 4));
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 16; k++) {
-                            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                            umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), d1 + koff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                            umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), d2 + koff, idesc, 1u);
-                        }
-                        umma_commit(&empty[s]);
-                        continue;
-                    }
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
-                        if (SPLIT_A) {
-                            umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, first);
-                            umma_bf16(tmem_d, d1 + koff, d2 + koff, idesc, 1u);
-                        } else {
-                            umma_bf16(tmem_d, d0 + koff, d1 + koff, idesc, first);
-                            umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, 1u);
-                        }
-                    }
-                    umma_commit(&empty[s]);
-                }
-                umma_commit(&acc_full[acc]);
-            }
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue =====
-        const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-        const int ehalf = (warp - 4) >> 2;      // which half of the tile's columns this warp drains
-        constexpr int ECOLS = TC_BN / 2;        // 96 columns per epilogue warp
-        int wl = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int m_tile, n_tile;
-            decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
-            const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
-            float *out = D + row * ldd + (int64_t)n_tile * TC_BN + ehalf * ECOLS;
-            // chunk sums are promoted into registers (IEEE round-to-nearest adds); one store per tile
-            float accr[ECOLS / 32][32];
-            for (int c = 0; c < n_chunks; c++, wl++) {
-                const int acc = wl & 1;
-                mbar_wait_bounded(&acc_full[acc], (uint32_t)((wl >> 1) & 1));
-                tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < ECOLS / 32; cc++) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                           (uint32_t)(acc * TC_BN + ehalf * ECOLS + cc * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-                          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-                          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int u = 0; u < 32; u++)
-                        accr[cc][u] = (c == 0) ? __uint_as_float(v[u]) : accr[cc][u] + __uint_as_float(v[u]);
-                }
-                // accumulator drained: hand it back to the MMA issuer
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acc]);
-            }
-#pragma unroll
-            for (int cc = 0; cc < ECOLS / 32; cc++)
-#pragma unroll
-                for (int u = 0; u < 32; u += 4)
-                    __stcs(reinterpret_cast<float4 *>(out + cc * 32 + u),      // streaming: do not pollute L2
-                           make_float4(accr[cc][u], accr[cc][u + 1], accr[cc][u + 2], accr[cc][u + 3]));
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Fused forward: logits GEMM with the softmax / residual epilogue on the accumulator.
-//   D[n, (i,a)] = sum_(j,b) X[n,(j,b)] * (Wp_hi + Wp_lo)[(i,a),(j,b)]        sequences on M (one TMEM lane each)
-// An N tile is 8 sites in two halves of 4 x 21 + 4 zero columns (UMMA N = 176); each of the 8 epilogue warps owns 32
-// sequences x 4 sites, so a thread sees whole 21-state logit vectors of its sequence: +h, softmax, fx,
-// residuals, bf16 hi/lo split written transposed (sequence fastest) straight into the operand of the backward
-// GEMM.  The 847 MB logits matrix never exists.  Per-(site, 32-sequence group) partials of g_h / fx keep the
-// reduction deterministic.
-// ---------------------------------------------------------------------------------------------------
-constexpr int TF_BN = 176;                         // 8 sites x 21 states + 8 pad
-constexpr int TF_SITES = 8;
-constexpr int TF_B_BYTES = TF_BN * TC_BK * 2;      // 22528
-constexpr int TF_STAGE = TC_A_BYTES + 2 * TF_B_BYTES;   // 61440
-
 template <int NCOL>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *v);
 template <>
@@ -417,6 +182,205 @@ __device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t *v)
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent GEMM with a double-buffered TMEM accumulator (2 x 192 columns): the epilogue of work item t
+// overlaps the main loop of work item t+1.
+//     forward  (SPLIT_A = 1)  Zt[(i,a), n]     = sum_(j,b) (Wt_hi [+ Wt_lo])[(i,a),(j,b)] * X[n,(j,b)]
+//     backward (SPLIT_A = 0)  Gd[(j,b),(i,a)]  = sum_n     Xt[(j,b), n] * (Rt_hi [+ Rt_lo])[(i,a), n]
+// Stage layout (the optional lo operand is LAST so that the bf16x1 precision mode uses a compact prefix and
+// a deeper ring): SPLIT_A = 1: [A_hi 16 KB][B 24 KB][A_lo 16 KB];  SPLIT_A = 0: [A 16 KB][B_hi 24 KB][B_lo 24 KB].
+// `single` != 0 (precision mode 1, "bf16 tiles"): the lo operand is neither loaded nor multiplied -- one
+// tcgen05.mma per K slice instead of two.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Tile enumeration: M tiles are swept in groups of `mgroup`; inside a group the M index is fastest, then the N
+// tile.  For the forward product (SPLIT_A) a group of M tiles whose slice of the coupling operand fits in L2
+// (about 24 MB, see plm_tcf_logits) stays resident while every sequence tile passes by; the backward uses one
+// group (all CTAs advance along K together and share operand tiles in time).
+__device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, int mgroup, int &m_tile, int &n_tile)
+{
+    const int full = (m_tiles / mgroup) * mgroup * n_tiles;
+    if (tile < full) {
+        const int per = mgroup * n_tiles;
+        const int g = tile / per, r = tile - g * per;
+        n_tile = r / mgroup;
+        m_tile = g * mgroup + (r - n_tile * mgroup);
+    } else {
+        const int rem = m_tiles % mgroup, r = tile - full;
+        n_tile = r / rem;
+        m_tile = (m_tiles / mgroup) * mgroup + (r - n_tile * rem);
+    }
+}
+
+template <int SPLIT_A>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                          const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
+                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int mgroup, int single, int n_stages)
+{
+    // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
+    // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
+    // 782 k-blocks); accumulating at most k_chunk k-blocks in TMEM and adding the chunk results in the
+    // epilogue (IEEE round-to-nearest) keeps it at the level of a plain fp32 sum.
+    constexpr int BYTES0 = TC_A_BYTES;                              // operand 0: A_hi (fwd) / A (bwd), 128 rows
+    constexpr int BYTES1 = TC_B_BYTES;                              // operand 1: B (fwd) / B_hi (bwd), 192 rows
+    constexpr int BYTES2 = SPLIT_A ? TC_A_BYTES : TC_B_BYTES;       // operand 2: A_lo (fwd) / B_lo (bwd), optional
+    const int stage_bytes = BYTES0 + BYTES1 + (single ? 0 : BYTES2);
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem0 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                                             ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem0);
+    uint64_t *empty = full + TC_MAX_STAGES;
+    uint64_t *acc_full = empty + TC_MAX_STAGES;  // [2]
+    uint64_t *acc_empty = acc_full + 2;          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    unsigned char *smem = smem0 + 1024;          // operand ring, 1024-byte aligned (SWIZZLE_128B atoms)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+    const int n_chunks = (num_kb + k_chunk - 1) / k_chunk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 8);         // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        // SPLIT_A (forward): the coupling matrix (A_hi, A_lo) is re-read by every sequence tile -> evict_last
+        const uint64_t keep = l2_policy_evict_last();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int m_tile, n_tile;
+            decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait_bounded(&empty[s], ph ^ 1u);
+                unsigned char *st = smem + s * stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                if (SPLIT_A) {
+                    tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                    tma_load_2d(st + BYTES0, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                    if (!single) tma_load_2d_hint(st + BYTES0 + BYTES1, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                } else {
+                    tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
+                    tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                    if (!single) tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                }
+                if (++s == n_stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+        int s = 0, wl = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int c = 0; c < n_chunks; c++, wl++) {
+                const int acc = wl & 1;
+                mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((wl >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+                const int kb0 = c * k_chunk, kb1 = min(num_kb, kb0 + k_chunk);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait_bounded(&full[s], ph);
+                    tc_fence_after();
+                    unsigned char *st = smem + s * stage_bytes;
+                    const uint64_t d0 = make_desc_sw128(st);
+                    const uint64_t d1 = make_desc_sw128(st + BYTES0);
+                    const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                        // operand 0 is always the 128-row (A) tile, operand 1 the 192-row (B) tile
+                        umma_bf16(tmem_d, d0 + koff, d1 + koff, idesc, first);
+                        if (!single) {
+                            if (SPLIT_A) umma_bf16(tmem_d, d2 + koff, d1 + koff, idesc, 1u);     // A_lo * B
+                            else umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, 1u);             // A * B_lo
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+        const int ehalf = (warp - 4) >> 2;      // which half of the tile's columns this warp drains
+        constexpr int ECOLS = TC_BN / 2;        // 96 columns per epilogue warp
+        int wl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int m_tile, n_tile;
+            decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
+            const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
+            float *out = D + row * ldd + (int64_t)n_tile * TC_BN + ehalf * ECOLS;
+            // chunk sums live in registers, added 16 columns at a time (IEEE round-to-nearest adds); one
+            // streaming store per tile
+            float accr[ECOLS];
+            for (int c = 0; c < n_chunks; c++, wl++) {
+                const int acc = wl & 1;
+                mbar_wait_bounded(&acc_full[acc], (uint32_t)((wl >> 1) & 1));
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                       (uint32_t)(acc * TC_BN + ehalf * ECOLS);
+#pragma unroll
+                for (int cc = 0; cc < ECOLS / 16; cc++) {
+                    uint32_t v[16];
+                    tmem_ld_cols<16>(taddr + cc * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        accr[cc * 16 + u] = (c == 0) ? __uint_as_float(v[u]) : accr[cc * 16 + u] + __uint_as_float(v[u]);
+                }
+                // accumulator drained: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            }
+#pragma unroll
+            for (int u = 0; u < ECOLS; u += 4)
+                __stcs(reinterpret_cast<float4 *>(out + u),      // streaming: do not pollute L2
+                       make_float4(accr[u], accr[u + 1], accr[u + 2], accr[u + 3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused forward: logits GEMM with the softmax / residual epilogue on the accumulator.
+//   D[n, (i,a)] = sum_(j,b) X[n,(j,b)] * (Wp_hi + Wp_lo)[(i,a),(j,b)]        sequences on M (one TMEM lane each)
+// An N tile is 8 sites in two halves of 4 x 21 + 4 zero columns (UMMA N = 176); each of the 8 epilogue warps owns 32
+// sequences x 4 sites, so a thread sees whole 21-state logit vectors of its sequence: +h, softmax, fx,
+// residuals, bf16 hi/lo split written transposed (sequence fastest) straight into the operand of the backward
+// GEMM.  The 847 MB logits matrix never exists.  Per-(site, 32-sequence group) partials of g_h / fx keep the
+// reduction deterministic.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TF_BN = 176;                         // 8 sites x 21 states + 8 pad
+constexpr int TF_SITES = 8;
+constexpr int TF_B_BYTES = TF_BN * TC_BK * 2;      // 22528
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
@@ -424,24 +388,26 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     const uint32_t *__restrict__ msa4, const float *__restrict__ wts,
                     __nv_bfloat16 *__restrict__ Rt_hi, __nv_bfloat16 *__restrict__ Rt_lo, int64_t Kp,
                     float *__restrict__ gh_part, double *__restrict__ fx_part, PlmGeom g, int m_tiles, int n_tiles,
-                    int num_kb, int a_tmem)
+                    int num_kb, int single, int n_stages)
 {
     constexpr int Q = 21;                          // states per site of this instantiation (q = 21 or 20 -> S = 21)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                                             ~static_cast<uintptr_t>(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TF_STAGE);
-    uint64_t *empty = full + TC_STAGES;
-    uint64_t *acc_full = empty + TC_STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + TC_MAX_STAGES;
+    uint64_t *acc_full = empty + TC_MAX_STAGES;
     uint64_t *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    smem += 1024;                                  // operand ring: [X 16 KB][W_hi 22 KB][W_lo 22 KB (hi+lo mode only)]
+    const int stage_bytes = TC_A_BYTES + TF_B_BYTES + (single ? 0 : TF_B_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
     const int q = g.q;                             // 21, or 20 with the ignored gap (column 20 of a site is then zero)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) {
+        for (int s = 0; s < n_stages; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -460,58 +426,46 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: tiles enumerated with the site tile fastest => concurrent CTAs share X tiles =====
         const uint64_t keep = l2_policy_evict_last();
-        int it = 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
-            for (int kb = 0; kb < num_kb; kb++, it++) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+            for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait_bounded(&empty[s], ph ^ 1u);
-                unsigned char *st = smem + s * TF_STAGE;
-                mbar_expect_tx(&full[s], TF_STAGE);
+                unsigned char *st = smem + s * stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
                 tma_load_2d(st, &tm_x, kb * TC_BK, m_tile * TC_BM, &full[s]);
                 tma_load_2d_hint(st + TC_A_BYTES, &tm_whi, kb * TC_BK, n_tile * TF_BN, &full[s], keep);
-                tma_load_2d_hint(st + TC_A_BYTES + TF_B_BYTES, &tm_wlo, kb * TC_BK, n_tile * TF_BN, &full[s], keep);
+                if (!single)
+                    tma_load_2d_hint(st + TC_A_BYTES + TF_B_BYTES, &tm_wlo, kb * TC_BK, n_tile * TF_BN, &full[s], keep);
+                if (++s == n_stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TF_BN);
-        int it = 0, tl = 0;
+        int s = 0, tl = 0;
+        uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tl++) {
             const int acc = tl & 1;
             mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((tl >> 1) & 1) ^ 1));
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TF_BN);
-            for (int kb = 0; kb < num_kb; kb++, it++) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+            for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait_bounded(&full[s], ph);
                 tc_fence_after();
-                unsigned char *st = smem + s * TF_STAGE;
+                unsigned char *st = smem + s * stage_bytes;
                 const uint64_t da = make_desc_sw128(st);
                 const uint64_t dh = make_desc_sw128(st + TC_A_BYTES);
                 const uint64_t dl = make_desc_sw128(st + TC_A_BYTES + TF_B_BYTES);
-                if (a_tmem) {
-                    const uint32_t ta = tmem_base + 2u * TF_BN + (uint32_t)(s * 32);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++)
-                        tmem_cp_128x256b(ta + (uint32_t)(k * 8), da + (uint64_t)((k * 16 * 2) >> 4));
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                        umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_bf16_ts(tmem_d, ta + (uint32_t)(k * 8), dl + koff, idesc, 1u);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                        umma_bf16(tmem_d, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_bf16(tmem_d, da + koff, dl + koff, idesc, 1u);
-                    }
+                for (int k = 0; k < TC_BK / 16; k++) {
+                    const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                    umma_bf16(tmem_d, da + koff, dh + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    if (!single) umma_bf16(tmem_d, da + koff, dl + koff, idesc, 1u);
                 }
                 umma_commit(&empty[s]);
+                if (++s == n_stages) { s = 0; ph ^= 1u; }
             }
             umma_commit(&acc_full[acc]);
         }
@@ -535,7 +489,7 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             tmem_ld_cols<32>(t0 + 32, v + 32);
             tmem_ld_cols<16>(t0 + 64, v + 64);
             tmem_ld_cols<4>(t0 + 80, v + 80);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld_wait();
             // logits are in registers: the accumulator can be reused by the MMA issuer right away
             tc_fence_before();
             __syncwarp();
@@ -571,7 +525,7 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                             const int64_t off = ((int64_t)i * q + a) * Kp + n;
                             const __nv_bfloat16 hi = __float2bfloat16_rn(r);
                             Rt_hi[off] = hi;
-                            Rt_lo[off] = __float2bfloat16_rn(r - __bfloat162float(hi));
+                            if (!single) Rt_lo[off] = __float2bfloat16_rn(r - __bfloat162float(hi));
                         }
                     }
                     const float tot = warp_sum(r);
@@ -589,7 +543,7 @@ tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 
 // expand for the fused forward: rows regrouped as [site tile][8 sites x q states (+ zero pad to 176)]
 __global__ void expand_tcf_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ Wp_hi,
-                                  __nv_bfloat16 *__restrict__ Wp_lo, int L, int q, int64_t ldw)
+                                  __nv_bfloat16 *__restrict__ Wp_lo, int L, int q, int64_t ldw, int single)
 {
     const int i = blockIdx.y, j = blockIdx.x;
     if (j <= i) return;
@@ -604,14 +558,15 @@ __global__ void expand_tcf_kernel(const float *__restrict__ x, __nv_bfloat16 *__
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const int64_t p1 = (ri + a) * ldw + (j * q + b);        // row (i,a), K index (j,b)
         const int64_t p2 = (rj + b) * ldw + (i * q + a);        // row (j,b), K index (i,a)
-        Wp_hi[p1] = hi; Wp_lo[p1] = lo;
-        Wp_hi[p2] = hi; Wp_lo[p2] = lo;
+        Wp_hi[p1] = hi;
+        Wp_hi[p2] = hi;
+        if (!single) { Wp_lo[p1] = lo; Wp_lo[p2] = lo; }
     }
 }
 
 // expand for the tensor-core forward: Wt[(i,a)][(j,b)] = J_ij(a,b) as bf16 hi + lo, both orientations
 __global__ void expand_tc_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ Wt_hi,
-                                 __nv_bfloat16 *__restrict__ Wt_lo, int L, int q, int64_t ldw)
+                                 __nv_bfloat16 *__restrict__ Wt_lo, int L, int q, int64_t ldw, int single)
 {
     const int i = blockIdx.y, j = blockIdx.x;
     if (j <= i) return;
@@ -623,8 +578,9 @@ __global__ void expand_tc_kernel(const float *__restrict__ x, __nv_bfloat16 *__r
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const int64_t p1 = (int64_t)(i * q + a) * ldw + (j * q + b);
         const int64_t p2 = (int64_t)(j * q + b) * ldw + (i * q + a);
-        Wt_hi[p1] = hi; Wt_lo[p1] = lo;
-        Wt_hi[p2] = hi; Wt_lo[p2] = lo;
+        Wt_hi[p1] = hi;
+        Wt_hi[p2] = hi;
+        if (!single) { Wt_lo[p1] = lo; Wt_lo[p2] = lo; }
     }
 }
 
@@ -641,50 +597,77 @@ __global__ void build_x_kernel(const uint32_t *__restrict__ msa4, __nv_bfloat16 
     }
 }
 
-// softmax + residuals from the logits Zt[(i,a)][n] (thread = sequence, fully coalesced)
-template <int Q>
-__global__ void __launch_bounds__(256)
+// softmax + residuals from the logits Zt[(i,a)][n]: thread = two adjacent sequences (8-byte loads of the
+// logits, 4-byte bf16x2 stores of the residuals), CTA = 128 threads = 256 sequences of one site.
+// ONEHOT = true: the "residual" is w_n [s_ni = a] (no logits read) -- the operand of the weighted pair counts
+// f_ij = sum_n w_n [s_ni = a][s_nj = b] computed by the same tensor-core backward product (row a6).
+template <int Q, bool ONEHOT>
+__global__ void __launch_bounds__(128)
 plm_softmax_kernel(const float *__restrict__ Zt, int64_t ldz, const float *__restrict__ h,
                    const uint32_t *__restrict__ msa4, const float *__restrict__ wts,
                    __nv_bfloat16 *__restrict__ Rt_hi, __nv_bfloat16 *__restrict__ Rt_lo, int64_t Kp,
                    float *__restrict__ gh_part, double *__restrict__ fx_part, PlmGeom g, int ntiles)
 {
-    __shared__ float s_gh[8 * 32];
-    __shared__ double s_fx[8];
+    __shared__ float s_gh[4 * 32];
+    __shared__ double s_fx[4];
     const int tile = blockIdx.x, i = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t N = g.N;
-    const int64_t n = (int64_t)tile * 256 + tid;
-    const int64_t m = n < N ? n : N - 1;
-    float z[Q];
-    float mx = -INFINITY;
+    const int64_t n0 = (int64_t)tile * 256 + 2 * tid;
+    // clamped, even load position (rows of Zt / msa4 are padded beyond N, see plm_tcf_geometry / plm_pack_msa)
+    const int64_t m0 = n0 < N ? n0 : ((N - 1) & ~(int64_t)1);
+    const uint2 wi = *reinterpret_cast<const uint2 *>(msa4 + (int64_t)(i >> 2) * g.Nld + m0);
+    const int sh = 8 * (i & 3);
+    const int si[2] = {(int)((wi.x >> sh) & 0xffu), (int)((wi.y >> sh) & 0xffu)};
+    float w[2];
+    w[0] = (n0 < N && si[0] < Q) ? wts[n0] : 0.f;
+    w[1] = (n0 + 1 < N && si[1] < Q) ? wts[n0 + 1] : 0.f;
+    float z[2][Q];
+    double fx_local = 0.0;
+    if (ONEHOT) {
 #pragma unroll
-    for (int a = 0; a < Q; a++) {
-        z[a] = Zt[((int64_t)i * Q + a) * ldz + m] + h[i * Q + a];
-        mx = fmaxf(mx, z[a]);
-    }
-    const uint32_t wi = msa4[(int64_t)(i >> 2) * g.Nld + m];
-    const int si = (int)((wi >> (8 * (i & 3))) & 0xffu);
-    const float w = (n < N && si < Q) ? wts[m] : 0.f;
-    float zs = 0.f, sum = 0.f;
+        for (int k = 0; k < 2; k++)
 #pragma unroll
-    for (int a = 0; a < Q; a++) {
-        if (a == si) zs = z[a];
-        z[a] = expf(z[a] - mx);
-        sum += z[a];
-    }
-    const double fx_local = (w == 0.f) ? 0.0 : -((double)w * (double)(zs - mx - logf(sum)));
-    const float inv = w / sum;
+            for (int a = 0; a < Q; a++) z[k][a] = (a == si[k]) ? w[k] : 0.f;
+    } else {
+        float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int a = 0; a < Q; a++) {
-        z[a] = z[a] * inv - (a == si ? w : 0.f);
-        if (n < N) {
-            const int64_t off = ((int64_t)i * Q + a) * Kp + n;
-            const __nv_bfloat16 hi = __float2bfloat16_rn(z[a]);
-            Rt_hi[off] = hi;
-            Rt_lo[off] = __float2bfloat16_rn(z[a] - __bfloat162float(hi));
+        for (int a = 0; a < Q; a++) {
+            const float2 v = *reinterpret_cast<const float2 *>(Zt + ((int64_t)i * Q + a) * ldz + m0);
+            const float ha = h[i * Q + a];
+            z[0][a] = v.x + ha;
+            z[1][a] = v.y + ha;
+            mx[0] = fmaxf(mx[0], z[0][a]);
+            mx[1] = fmaxf(mx[1], z[1][a]);
         }
-        const float v = warp_sum(z[a]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            float zs = 0.f, sum = 0.f;
+#pragma unroll
+            for (int a = 0; a < Q; a++) {
+                if (a == si[k]) zs = z[k][a];
+                z[k][a] = expf(z[k][a] - mx[k]);
+                sum += z[k][a];
+            }
+            if (w[k] != 0.f) fx_local -= (double)w[k] * (double)(zs - mx[k] - logf(sum));
+            const float inv = w[k] / sum;
+#pragma unroll
+            for (int a = 0; a < Q; a++) z[k][a] = z[k][a] * inv - (a == si[k] ? w[k] : 0.f);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < Q; a++) {
+        if (n0 < N) {
+            // n0 is even and Kp is a multiple of 64: the pair (n0, n0 + 1) is 4-byte aligned and inside the row;
+            // a sequence beyond N has weight 0, i.e. writes an exact zero into the K padding
+            const int64_t off = ((int64_t)i * Q + a) * Kp + n0;
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(z[0][a], z[1][a]);
+            *reinterpret_cast<__nv_bfloat162 *>(Rt_hi + off) = hi;
+            if (Rt_lo != nullptr)
+                *reinterpret_cast<__nv_bfloat162 *>(Rt_lo + off) =
+                    __floats2bfloat162_rn(z[0][a] - __low2float(hi), z[1][a] - __high2float(hi));
+        }
+        const float v = warp_sum(z[0][a] + z[1][a]);
         if (lane == 0) s_gh[warp * 32 + a] = v;
     }
     const double fw = warp_sum(fx_local);
@@ -693,14 +676,10 @@ plm_softmax_kernel(const float *__restrict__ Zt, int64_t ldz, const float *__res
     if (tid < g.S) {
         float tot = 0.f;
         if (tid < Q)
-            for (int ww = 0; ww < 8; ww++) tot += s_gh[ww * 32 + tid];
+            for (int ww = 0; ww < 4; ww++) tot += s_gh[ww * 32 + tid];
         gh_part[((int64_t)i * ntiles + tile) * g.S + tid] = tot;
     }
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int ww = 0; ww < 8; ww++) tot += s_fx[ww];
-        fx_part[(int64_t)i * ntiles + tile] = tot;
-    }
+    if (tid == 0) fx_part[(int64_t)i * ntiles + tile] = (s_fx[0] + s_fx[1]) + (s_fx[2] + s_fx[3]);
 }
 
 // ---- one-hot operand (static per MSA) ----------------------------------------------------------------
@@ -732,26 +711,34 @@ __global__ void finalize_pairs_tc_kernel(const float *__restrict__ Gd, float *__
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-static int a_tmem_enabled()
+// tuning hooks for parameter sweeps (read once; the defaults below are what the product uses)
+static int env_int_once(const char *name, int *cache)
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("EVC_A_TMEM");
-        v = e ? atoi(e) : 0;
+    if (*cache == -2) {
+        const char *e = getenv(name);
+        *cache = e ? atoi(e) : -1;
     }
-    return v;
+    return *cache;
 }
 
-static int sm_count_cached()
+static int sm_count_current()
 {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!cache[dev]) {
+        int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+        cache[dev] = n > 0 ? n : 148;
     }
-    return n;
+    return cache[dev];
+}
+
+// ring depth for a given stage size: as many stages as fit in the 227 KB opt-in shared memory
+static int stages_for(int stage_bytes)
+{
+    return std::max(2, std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - TC_SMEM_HEAD) / stage_bytes));
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -813,16 +800,21 @@ int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_l
     return 0;
 }
 
-int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, float *d_Gd, cudaStream_t st)
+int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, float *d_Gd, int single, cudaStream_t st)
 {
     const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 128;
+    const int stage = TC_A_BYTES + TC_B_BYTES + (single ? 0 : TC_B_BYTES);
+    const int n_stages = stages_for(stage);
+    const size_t smem = (size_t)n_stages * stage + TC_SMEM_HEAD;
     EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+                                  TC_SMEM_LIMIT));
+    static int kc_env = -2;
+    const int kc = env_int_once("EVC_KCHUNK", &kc_env);
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Np / TC_BN);
-    const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
+    const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
-                                                                (int)(t.Kp / TC_BK), TC_K_CHUNK, a_tmem_enabled(), m_tiles);
+                                                                (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK,
+                                                                m_tiles, single, n_stages);
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -866,26 +858,63 @@ int plm_tcf_make_maps(const PlmTcfGeom &t, void *d_wt_hi, void *d_wt_lo, void *d
 }
 
 int plm_tcf_expand(const PlmGeom &g, const PlmTcfGeom &t, const float *d_x, void *d_wt_hi, void *d_wt_lo,
-                   cudaStream_t st)
+                   int single, cudaStream_t st)
 {
     dim3 grid((unsigned)g.L, (unsigned)g.L);
     expand_tc_kernel<<<grid, 128, 0, st>>>(d_x, reinterpret_cast<__nv_bfloat16 *>(d_wt_hi),
-                                          reinterpret_cast<__nv_bfloat16 *>(d_wt_lo), g.L, g.q, t.Kw);
+                                          reinterpret_cast<__nv_bfloat16 *>(d_wt_lo), g.L, g.q, t.Kw, single);
     EVC_KERNEL_CHECK();
     return 0;
 }
 
-int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, float *d_zt, cudaStream_t st)
+// M tiles per group of the forward tile order: the group's slice of the coupling operand (hi [+ lo], all of
+// K) should stay L2-resident while every sequence tile passes by.  24 MB per group measured best at config 2
+// (71 MB operand); for long alignments (L = 500: 441 MB, L = 800: 1.13 GB) the same byte budget
+// gives groups of 4 / 2 M tiles instead of the fixed 11 that round 1 used.
+static int forward_mgroup(const PlmTcfGeom &t, int single, int m_tiles)
+{
+    static int mg_env = -2;
+    const int e = env_int_once("EVC_MGROUP", &mg_env);
+    if (e > 0) return std::min(e, m_tiles);
+    static int mb_env = -2;
+    const int mb = env_int_once("EVC_MGROUP_MB", &mb_env);
+    const double budget = (mb > 0 ? mb : 24) * 1.0e6;
+    const double per_tile = (double)TC_BM * (double)t.Kw * 2.0 * (single ? 1.0 : 2.0);
+    return std::max(1, std::min(m_tiles, (int)(budget / per_tile)));
+}
+
+int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, float *d_zt, int single, cudaStream_t st)
 {
     const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
-    const size_t smem = (size_t)TC_STAGES * (2 * TC_A_BYTES + TC_B_BYTES) + 1024 + 128;
+    const int stage = TC_A_BYTES + TC_B_BYTES + (single ? 0 : TC_A_BYTES);
+    const int n_stages = stages_for(stage);
+    const size_t smem = (size_t)n_stages * stage + TC_SMEM_HEAD;
     EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+                                  TC_SMEM_LIMIT));
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Ns / TC_BN);
-    const int grid = std::min(sm_count_cached(), m_tiles * n_tiles);
+    const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     const int num_kb = (int)(t.Kw / TC_BK);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
-                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK, 0, std::min(m_tiles, 11));
+                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK,
+                                                                forward_mgroup(t, single, m_tiles), single, n_stages);
+    EVC_KERNEL_CHECK();
+    return 0;
+}
+
+// softmax / residual kernel; d_rt_lo == nullptr in the bf16x1 precision mode (no lo operand is written)
+template <bool ONEHOT>
+static int launch_softmax(const PlmGeom &g, int ntiles, const float *d_zt, int64_t ldz, const float *d_x,
+                          const uint32_t *d_msa4, const float *d_wts, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
+                          int64_t Kp, float *d_gh_part, double *d_fx_part, cudaStream_t st)
+{
+    dim3 grid((unsigned)ntiles, (unsigned)g.L);
+    switch (g.q) {
+        case 21: plm_softmax_kernel<21, ONEHOT><<<grid, 128, 0, st>>>(d_zt, ldz, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, ntiles); break;
+        case 20: plm_softmax_kernel<20, ONEHOT><<<grid, 128, 0, st>>>(d_zt, ldz, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, ntiles); break;
+        case 5: plm_softmax_kernel<5, ONEHOT><<<grid, 128, 0, st>>>(d_zt, ldz, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, ntiles); break;
+        case 4: plm_softmax_kernel<4, ONEHOT><<<grid, 128, 0, st>>>(d_zt, ldz, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, ntiles); break;
+        default: set_error("plm softmax kernel: unsupported q"); return 1;
+    }
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -894,17 +923,19 @@ int plm_tcf_softmax(const PlmGeom &g, const PlmTcfGeom &t, const float *d_zt, co
                     const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
                     float *d_gh_part, double *d_fx_part, cudaStream_t st)
 {
-    dim3 grid((unsigned)t.ntiles_s, (unsigned)g.L);
-    __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(d_rt_hi), *lo = reinterpret_cast<__nv_bfloat16 *>(d_rt_lo);
-    switch (g.q) {
-        case 21: plm_softmax_kernel<21><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
-        case 20: plm_softmax_kernel<20><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
-        case 5: plm_softmax_kernel<5><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
-        case 4: plm_softmax_kernel<4><<<grid, 256, 0, st>>>(d_zt, t.Ns, d_x, d_msa4, d_wts, hi, lo, Kp, d_gh_part, d_fx_part, g, t.ntiles_s); break;
-        default: set_error("plm_tcf_softmax: unsupported q"); return 1;
-    }
-    EVC_KERNEL_CHECK();
-    return 0;
+    return launch_softmax<false>(g, t.ntiles_s, d_zt, t.Ns, d_x, d_msa4, d_wts,
+                                 reinterpret_cast<__nv_bfloat16 *>(d_rt_hi), reinterpret_cast<__nv_bfloat16 *>(d_rt_lo),
+                                 Kp, d_gh_part, d_fx_part, st);
+}
+
+// a6 on the tensor cores: Rt = w_n [s_ni = a] as bf16 hi + lo (the weights keep 16 mantissa bits), per-tile
+// partials of f_i; the caller then runs the backward product and symmetrises with scale 0.5
+int plm_tc_onehot_residual(const PlmGeom &g, int ntiles, const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi,
+                           void *d_rt_lo, int64_t Kp, float *d_gh_part, double *d_fx_part, cudaStream_t st)
+{
+    return launch_softmax<true>(g, ntiles, nullptr, 0, nullptr, d_msa4, d_wts,
+                                reinterpret_cast<__nv_bfloat16 *>(d_rt_hi), reinterpret_cast<__nv_bfloat16 *>(d_rt_lo),
+                                Kp, d_gh_part, d_fx_part, st);
 }
 
 // ---- fused tensor-core forward ------------------------------------------------------------------------
@@ -930,27 +961,30 @@ int plm_tcff_make_maps(const PlmTcffGeom &t, void *d_x1h, void *d_wp_hi, void *d
 }
 
 int plm_tcff_expand(const PlmGeom &g, const PlmTcffGeom &t, const float *d_x, void *d_wp_hi, void *d_wp_lo,
-                    cudaStream_t st)
+                    int single, cudaStream_t st)
 {
     dim3 grid((unsigned)g.L, (unsigned)g.L);
     expand_tcf_kernel<<<grid, 128, 0, st>>>(d_x, reinterpret_cast<__nv_bfloat16 *>(d_wp_hi),
-                                           reinterpret_cast<__nv_bfloat16 *>(d_wp_lo), g.L, g.q, t.Kw);
+                                           reinterpret_cast<__nv_bfloat16 *>(d_wp_lo), g.L, g.q, t.Kw, single);
     EVC_KERNEL_CHECK();
     return 0;
 }
 
 int plm_tcff_forward(const PlmGeom &g, const PlmTcffGeom &t, const void *maps, const float *d_x,
                      const uint32_t *d_msa4, const float *d_wts, void *d_rt_hi, void *d_rt_lo, int64_t Kp,
-                     float *d_gh_part, double *d_fx_part, cudaStream_t st)
+                     float *d_gh_part, double *d_fx_part, int single, cudaStream_t st)
 {
     const CUtensorMap *m = reinterpret_cast<const CUtensorMap *>(maps);
-    const size_t smem = (size_t)TC_STAGES * TF_STAGE + 1024 + 128;
-    EVC_CUDA(cudaFuncSetAttribute(tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(sm_count_cached(), t.m_tiles * t.n_tiles);
+    const int stage = TC_A_BYTES + TF_B_BYTES + (single ? 0 : TF_B_BYTES);
+    const int n_stages = stages_for(stage);
+    const size_t smem = (size_t)n_stages * stage + TC_SMEM_HEAD;
+    EVC_CUDA(cudaFuncSetAttribute(tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    const int grid = std::min(sm_count_current(), t.m_tiles * t.n_tiles);
     tc_fwd_fused_kernel<<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_x, d_msa4, d_wts,
                                                         reinterpret_cast<__nv_bfloat16 *>(d_rt_hi),
                                                         reinterpret_cast<__nv_bfloat16 *>(d_rt_lo), Kp, d_gh_part,
-                                                        d_fx_part, g, t.m_tiles, t.n_tiles, (int)(t.Kw / TC_BK), a_tmem_enabled());
+                                                        d_fx_part, g, t.m_tiles, t.n_tiles, (int)(t.Kw / TC_BK), single,
+                                                        n_stages);
     EVC_KERNEL_CHECK();
     return 0;
 }

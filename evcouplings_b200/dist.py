@@ -21,11 +21,11 @@ def shard_bounds(n, world, rank):
 class Collective(object):
     """Thin wrapper over torch.distributed that degrades to a no-op for a single process."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, standalone=False):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
-        if dist.is_available() and dist.is_initialized():
+        if not standalone and dist.is_available() and dist.is_initialized():
             self.rank = dist.get_rank(group)
             self.world = dist.get_world_size(group)
         else:

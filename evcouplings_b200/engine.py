@@ -23,6 +23,11 @@ from . import lbfgs as _lbfgs
 # backward implementation of the data term: "gather" (shared-memory bucket kernel) or "tc" (tcgen05 GEMM)
 DEFAULT_BACKWARD = "tc"
 DEFAULT_FORWARD = "tc"
+# arithmetic of the tensor-core products: "fp32" (bf16 hi+lo pairs, fp32-equivalent; default), "bf16" (one bf16
+# product, BASELINE configs[4] "bf16 tiles / fp32 parameters"), "auto" (fit only: bf16 until close to convergence,
+# then fp32 to the end)
+DEFAULT_PRECISION = "fp32"
+PRECISIONS = ("fp32", "bf16", "auto")
 
 
 def _torch():
@@ -34,13 +39,15 @@ from .dist import Collective, shard_bounds   # noqa: E402,F401
 
 
 class CudaEngine(object):
-    def __init__(self, device=None, group=None):
+    def __init__(self, device=None, group=None, standalone=False):
+        """``standalone=True``: ignore an initialised torch.distributed group (this process works alone on its
+        GPU, e.g. rank 0 checking a sharded result against a single-GPU evaluation)."""
         self.lib = _lib.load()
         _lib.require_device()
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.EngineUnavailableError("torch sees no CUDA device; the PLM engine has no CPU fallback")
-        self.coll = Collective(group)
+        self.coll = Collective(group, standalone=standalone)
         self.rank, self.world = self.coll.rank, self.coll.world
         if device is None:
             device = torch.cuda.current_device()
@@ -55,6 +62,14 @@ class CudaEngine(object):
 
     def all_reduce(self, tensor):
         self.coll.all_reduce_sum(tensor)
+
+    def agree_any(self, flag):
+        """True on every rank if ``flag`` is true on any rank (doubles as the barrier after rank 0 wrote files)."""
+        if self.world == 1:
+            return bool(flag)
+        t = _torch().tensor([1 if flag else 0], dtype=_torch().int32, device=self.device)
+        self.coll.all_reduce_max(t)
+        return bool(int(t.item()))
 
     @staticmethod
     def ptr(t):
@@ -89,8 +104,17 @@ class CudaEngine(object):
         return d_counts
 
     # -- (a) PLM ---------------------------------------------------------------------------
-    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None, forward=None):
-        return CudaPlmProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m, backward, forward)
+    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None, forward=None,
+                    precision=None):
+        return CudaPlmProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m, backward, forward, precision)
+
+
+class _DevicePointer(object):
+    """Zero-copy torch view of library-owned device memory (CUDA array interface)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
 
 
 class CudaPlmProblem(object):
@@ -98,8 +122,13 @@ class CudaPlmProblem(object):
     (see lbfgs.py for the protocol).  All n-vectors are torch CUDA tensors."""
 
     def __init__(self, engine, codes, weights, q, gap_code, lambda_h, lambda_J, m=6, backward=None,
-                 forward=None):
+                 forward=None, precision=None):
         torch = _torch()
+        if precision is None:
+            precision = os.environ.get("EVC_PRECISION", DEFAULT_PRECISION)
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
+        self.precision = precision
         if forward is None:
             forward = os.environ.get("EVC_FORWARD", DEFAULT_FORWARD)
         if forward not in ("gather", "tc", "tcfused"):
@@ -119,6 +148,9 @@ class CudaPlmProblem(object):
         N, L = codes.shape
         if weights.shape != (N,):
             raise ValueError("weights must have one entry per sequence")
+        n_states = int(q) + (1 if int(gap_code) >= 0 else 0)
+        if N and int(codes.max()) >= n_states:
+            raise ValueError("sequence codes must be < %d (q%s)" % (n_states, " + ignored gap" if gap_code >= 0 else ""))
         self.N_total, self.L, self.q, self.gap_code = N, L, int(q), int(gap_code)
         self.lambda_h, self.lambda_J = float(lambda_h), float(lambda_J)
         lo, hi = shard_bounds(N, engine.world, engine.rank)
@@ -137,19 +169,17 @@ class CudaPlmProblem(object):
         if forward in ("tc", "tcfused"):
             _lib.check(self.lib.evc_plm_set_forward(self.handle, 2 if forward == "tcfused" else 1),
                        "evc_plm_set_forward")
+        if precision == "bf16":
+            _lib.check(self.lib.evc_plm_set_precision(self.handle, 1), "evc_plm_set_precision")
         self.n = int(self.lib.evc_plm_num_params(self.handle))
         dev = engine.device
         self.m = m
         f32 = dict(dtype=torch.float32, device=dev)
         self.x = torch.zeros(self.n, **f32)
-        self.g = torch.zeros(self.n, **f32)
-        self.xp = torch.zeros(self.n, **f32)
-        self.gp = torch.zeros(self.n, **f32)
-        self.d = torch.zeros(self.n, **f32)
-        self.S = torch.zeros((m, self.n), **f32)
-        self.Y = torch.zeros((m, self.n), **f32)
-        self.ys = torch.zeros(m, dtype=torch.float64, device=dev)
-        self.scratch = torch.zeros(m + 2, dtype=torch.float64, device=dev)
+        # gradient + 4 trailing floats: -loglk rides behind g as exact fixed-point limbs => ONE all-reduce
+        self.g_packed = torch.zeros(self.n + 4, **f32)
+        self.g = self.g_packed[:self.n]
+        self._python_space = False          # vectors of the Python L-BFGS driver are allocated on demand
         self.fxbuf = torch.zeros(2, dtype=torch.float64, device=dev)
         self.dotbuf = torch.zeros(1, dtype=torch.float64, device=dev)
         self.last_negloglk = float("nan")
@@ -175,8 +205,11 @@ class CudaPlmProblem(object):
         _lib.check(self.lib.evc_plm_eval_data(self.handle, p(x), p(self.g), p(self.fxbuf), e.stream()),
                    "evc_plm_eval_data")
         if e.world > 1:
-            e.all_reduce(self.g)
-            e.all_reduce(self.fxbuf[0:1])
+            limbs = self.g_packed[self.n:]
+            _lib.check(self.lib.evc_plm_pack_fx(p(self.fxbuf), p(limbs), e.stream()), "evc_plm_pack_fx")
+            e.all_reduce(self.g_packed)                     # ONE collective: [g, -loglk]
+            _lib.check(self.lib.evc_plm_unpack_fx(p(limbs), p(self.fxbuf), e.stream()), "evc_plm_unpack_fx")
+            e.kernel_launches += 2
         _lib.check(self.lib.evc_plm_add_regulariser(self.handle, p(x), p(self.g), p(self.fxbuf),
                                                     self.lambda_h, self.lambda_J, e.stream()),
                    "evc_plm_add_regulariser")
@@ -199,7 +232,22 @@ class CudaPlmProblem(object):
         self.last_negloglk = nll
         return fx
 
-    # -- vector space protocol ------------------------------------------------------------------
+    # -- vector space protocol (Python L-BFGS driver, kept for comparison / tests) -------------------
+    def _ensure_python_space(self):
+        if self._python_space:
+            return
+        torch = _torch()
+        f32 = dict(dtype=torch.float32, device=self.engine.device)
+        m = self.m
+        self.xp = torch.zeros(self.n, **f32)
+        self.gp = torch.zeros(self.n, **f32)
+        self.d = torch.zeros(self.n, **f32)
+        self.S = torch.zeros((m, self.n), **f32)
+        self.Y = torch.zeros((m, self.n), **f32)
+        self.ys = torch.zeros(m, dtype=torch.float64, device=self.engine.device)
+        self.scratch = torch.zeros(m + 2, dtype=torch.float64, device=self.engine.device)
+        self._python_space = True
+
     def dot(self, a, b):
         e = self.engine
         _lib.check(self.lib.evc_vec_dot(e.ptr(a), e.ptr(b), self.n, e.ptr(self.dotbuf), e.stream()), "evc_vec_dot")
@@ -262,8 +310,11 @@ class CudaPlmProblem(object):
         return self.x.cpu().numpy()
 
     def norms(self):
-        """(|h|, |J|) of the current parameters (for the iteration table), via the library's dot kernels."""
+        """(|h|, |J|) of the current parameters (for the iteration table)."""
         import math
+        cached = getattr(self, "_cached_norms", None)
+        if cached is not None:                  # evc_plm_fit reports them with every iteration
+            return cached
         e = self.engine
         nh = self.L * self.q
         out = []
@@ -274,6 +325,67 @@ class CudaPlmProblem(object):
             out.append(math.sqrt(float(self.dotbuf.item())))
         return out[0], out[1]
 
-    def fit(self, x0, params, progress=None):
+    def fit(self, x0, params, progress=None, driver="device"):
+        """Minimise from x0.  driver "device": the whole L-BFGS loop runs inside libevcplm (evc_plm_fit);
+        "python": the same algorithm with host-side control (lbfgs.py), kept for comparison.
+        ``progress(k, fx, xnorm, gnorm, step, n_ls)``; returns lbfgs.LbfgsResult."""
         self.set_x(x0)
-        return _lbfgs.minimize(self, params, progress)
+        if driver == "python":
+            self._ensure_python_space()
+            self._cached_norms = None
+            return _lbfgs.minimize(self, params, progress)
+        return self._fit_device(params, progress)
+
+    def _fit_device(self, params, progress):
+        e, lib = self.engine, self.lib
+        torch = _torch()
+        fp = _lib.FitParams()
+        lib.evc_fit_default_params(ctypes.byref(fp))
+        fp.max_iterations, fp.m, fp.epsilon = int(params.max_iterations), int(params.m), float(params.epsilon)
+        fp.lambda_h, fp.lambda_J = self.lambda_h, self.lambda_J
+        fp.max_linesearch = int(params.max_linesearch)
+        fp.min_step, fp.max_step = float(params.min_step), float(params.max_step)
+        fp.ftol, fp.gtol, fp.xtol = float(params.ftol), float(params.gtol), float(params.xtol)
+        fp.precision_schedule = 1 if self.precision == "auto" else 0
+        errors = []
+        views = {}
+
+        def allreduce(user, d_buf, count, stream):
+            try:
+                key = (d_buf, count)
+                if key not in views:
+                    views[key] = torch.as_tensor(_DevicePointer(d_buf, count), device=e.device)
+                e.all_reduce(views[key])
+                return 0
+            except BaseException as exc:          # never let an exception cross the C boundary
+                errors.append(exc)
+                return 1
+
+        def on_iteration(user, k, fx, xnorm, gnorm, step, n_ls, nll, hnorm, enorm):
+            try:
+                self.last_negloglk = nll
+                self._cached_norms = (hnorm, enorm)
+                if progress is not None and progress(k, fx, xnorm, gnorm, step, n_ls):
+                    return 1
+                return 0
+            except BaseException as exc:
+                errors.append(exc)
+                return 1
+
+        ar_cb = _lib.ALLREDUCE_CB(allreduce) if e.world > 1 else None
+        pr_cb = _lib.PROGRESS_CB(on_iteration)
+        res = _lib.FitResult()
+        rc = lib.evc_plm_fit(self.handle, e.ptr(self.x), ctypes.byref(fp),
+                             ctypes.cast(ar_cb, ctypes.c_void_p) if ar_cb is not None else None, None,
+                             ctypes.cast(pr_cb, ctypes.c_void_p), None, ctypes.byref(res), e.stream())
+        self._cached_norms = None
+        if errors:
+            raise errors[0]
+        _lib.check(rc, "evc_plm_fit")
+        self.last_negloglk = res.negloglk
+        self.evaluations += res.evaluations
+        e.kernel_launches += res.evaluations * (self.launches_per_eval + 2)
+        self.fit_seconds = res.seconds
+        self.switched_at = res.switched_at
+        return _lbfgs.LbfgsResult(_lib.LBFGS_STATUS.get(res.status, "LBFGSERR_UNKNOWNERROR"), res.iterations,
+                                  res.fx, res.evaluations)

@@ -112,7 +112,10 @@ def hamiltonians(model, sequences, engine=None):
     if len(sequences) and isinstance(sequences[0], str):
         codes = encode_sequences(model, sequences)
     else:
-        codes = np.ascontiguousarray(sequences).astype(np.uint8)
+        arr = np.ascontiguousarray(sequences)
+        if arr.size and (arr.min() < 0 or arr.max() > model["q"]):
+            raise ValueError("mapped sequence symbols must be in [0, %d] (%d = gap)" % (model["q"], model["q"]))
+        codes = arr.astype(np.uint8)
     N, L = codes.shape
     q = model["q"]
     gap_code = q if int(codes.max(initial=0)) >= q else -1

@@ -16,6 +16,7 @@ by the golden run in the reference's notebooks/example/):
 The reference side of this boundary is evcouplings/couplings/tools.py:213-233
 (focus name passed with ``/range`` stripped, alphabet with gap first).
 """
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -42,9 +43,29 @@ class AlignmentError(ValueError):
 
 
 def read_fasta_matrix(path):
-    """Read FASTA/A2M into (ids, uint8 matrix n_total x width of raw characters).  Sequences may be wrapped over
-    several lines.  (A fully numpy-vectorised reader was tried for SURVEY 8f row f4 and was 40x SLOWER than this
-    line loop at N=500k -- 0.7 s for 259 MB -- so the line loop stays.)"""
+    """Read FASTA/A2M into (ids, uint8 matrix n_total x width of raw characters) with the compiled reader of
+    libevcplm (csrc/a2m_reader.cu: mmap + memchr).  Sequences may be wrapped over several lines."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    n_rows, width, ids_bytes = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    bpath = os.fsencode(path)
+    rc = lib.evc_a2m_scan(bpath, ctypes.byref(n_rows), ctypes.byref(width), ctypes.byref(ids_bytes))
+    if rc == 2:
+        raise AlignmentError(lib.evc_last_error().decode())
+    _lib.check(rc, "evc_a2m_scan")
+    raw = np.empty((n_rows.value, width.value), dtype=np.uint8)
+    idbuf = ctypes.create_string_buffer(max(1, ids_bytes.value))
+    rc = lib.evc_a2m_read(bpath, n_rows.value, width.value, raw.ctypes.data_as(ctypes.c_void_p), idbuf, ids_bytes.value)
+    if rc == 2:
+        raise AlignmentError(lib.evc_last_error().decode())
+    _lib.check(rc, "evc_a2m_read")
+    ids = idbuf.raw[:ids_bytes.value].decode("ascii", "replace").split("\0")[:n_rows.value]
+    return ids, raw
+
+
+def read_fasta_matrix_py(path):
+    """Pure-Python twin of read_fasta_matrix (kept as the cross-check of the compiled reader in the tests)."""
     ids, chunks, cur = [], [], None
     with open(path, "rb") as f:
         for line in f:
@@ -134,12 +155,7 @@ def encode_alignment(ids, raw, focus=None, alphabet=None, ignore_gaps=False):
     lut[ord(".")] = gcode
     for c in range(ord("a"), ord("z") + 1):      # case-insensitive (rows are upper-cased by plmc)
         lut[c] = lut[c - 32]
-    coded = lut[raw]                              # single pass over the whole alignment
-    valid = (coded != 255).all(axis=1)
-    if valid.all() and len(cols) == width:
-        codes = coded
-    else:
-        codes = np.ascontiguousarray(coded[valid][:, cols] if not valid.all() else coded[:, cols])
+    codes, valid = _encode_rows(raw, lut, cols)
     if focus_index is not None:
         target = bytes(upper[raw[focus_index, cols]]).decode("ascii")
     else:
@@ -150,6 +166,25 @@ def encode_alignment(ids, raw, focus=None, alphabet=None, ignore_gaps=False):
         target_seq=target, region_start=region_start, n_total=n_total,
         n_valid=int(valid.sum()), num_total_sites=num_total_sites,
     )
+
+
+def _encode_rows(raw, lut, cols):
+    """codes of the selected columns of the valid rows + the validity mask, by the compiled encoder
+    (evc_msa_encode: threaded, two passes over the character matrix)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    n_total, width = raw.shape
+    cols64 = np.ascontiguousarray(cols, dtype=np.int64)
+    valid8 = np.empty(n_total, dtype=np.uint8)
+    codes = np.empty((n_total, len(cols64)), dtype=np.uint8)
+    n_valid = ctypes.c_int64(0)
+    vp = ctypes.c_void_p
+    _lib.check(lib.evc_msa_encode(raw.ctypes.data_as(vp), n_total, width, lut.ctypes.data_as(vp),
+                                  cols64.ctypes.data_as(vp), len(cols64), valid8.ctypes.data_as(vp),
+                                  codes.ctypes.data_as(vp), ctypes.byref(n_valid)), "evc_msa_encode")
+    return codes[:n_valid.value], valid8.astype(bool)
 
 
 def load_alignment(path, focus=None, alphabet=None, ignore_gaps=False):

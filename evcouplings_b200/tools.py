@@ -139,22 +139,61 @@ def _default_engine():
     return CudaEngine()
 
 
+# single-GPU throughput used to decide whether spawning one rank per GPU pays (start-up of the ranks: ~15 s)
+_CELLS_PER_SECOND_1GPU = 8.0e12
+_MULTI_GPU_MIN_SECONDS = 20.0
+
+
+def _resolve_num_gpus(num_gpus, cpu, n_valid, L, q, max_iter):
+    """How many GPUs a single-process call should use.  The reference forwards ``cpu`` to plmc as ``-n``
+    (evcouplings/couplings/tools.py:257-259, utils/pipeline.py:92,187); here it caps the number of GPUs.
+    Explicit ``num_gpus`` / EVC_NUM_GPUS win; otherwise all visible GPUs are used when the estimated
+    single-GPU time of the fit exceeds the cost of starting the ranks."""
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return 1                    # this process already IS one rank of a multi-GPU job
+        visible = torch.cuda.device_count()
+    except Exception:
+        return 1
+    if visible <= 1:
+        return 1
+    env = os.environ.get("EVC_NUM_GPUS")
+    if num_gpus is None and env:
+        num_gpus = int(env)
+    if num_gpus is not None:
+        return max(1, min(int(num_gpus), visible))
+    cap = visible if cpu is None else max(1, min(int(cpu), visible))
+    iters = max_iter if max_iter else 200
+    est = float(n_valid) * L * L * q * iters / _CELLS_PER_SECOND_1GPU
+    return cap if est >= _MULTI_GPU_MIN_SECONDS else 1
+
+
 def run_plmc(alignment, couplings_file, param_file=None,
              focus_seq=None, alphabet=None, theta=None,
              scale=None, ignore_gaps=False, iterations=None,
              lambda_h=None, lambda_J=None, lambda_g=None,
              cpu=None, binary="plmc", engine=None, return_run=False,
-             epsilon=DEFAULT_EPSILON, history=DEFAULT_HISTORY, store_inverse_weights=False):
+             epsilon=DEFAULT_EPSILON, history=DEFAULT_HISTORY, store_inverse_weights=False,
+             precision=None, num_gpus=None):
     """
     Same parameters and return value as the reference's run_plmc
     (evcouplings/couplings/tools.py:126-194).  ``theta`` is the EVcouplings identity threshold
     (sequences with identity >= theta are clustered); ``lambda_J`` arrives already scaled by the
-    protocol (protocol.py:179); ``cpu`` and ``binary`` are accepted and ignored (the work runs on
-    the GPU(s) of the calling process / torch.distributed group).
+    protocol (protocol.py:179); ``binary`` is accepted and ignored.  ``cpu`` (plmc ``-n``, tools.py:257-259)
+    caps the number of GPUs: a plain single-process call on a multi-GPU box starts one rank per GPU itself
+    (evcouplings_b200.launcher) when the fit is long enough to pay for it; inside an initialised
+    torch.distributed group (torchrun) the call is one rank of that group.
 
     Extra keyword arguments (not in the reference): ``engine`` (a CudaEngine; default: create one,
     which fails loudly without libevcplm.so + a CUDA device), ``return_run`` (also return the
-    PlmcRun record), ``epsilon`` / ``history`` (L-BFGS stop criterion and memory).
+    PlmcRun record), ``epsilon`` / ``history`` (L-BFGS stop criterion and memory), ``precision``
+    ("fp32" default | "bf16" | "auto", see engine.PRECISIONS), ``num_gpus`` (explicit GPU count).
+
+    Trajectory note: plmc's L-BFGS start point, epsilon and history are recalled, not pinned (no plmc
+    source); with an iteration cap the written parameters depend on the optimiser path, so agreement with
+    a plmc run at the same cap is statistical, exact only at convergence.
     """
     run = PlmcRun()
     t_start = time.time()
@@ -195,6 +234,16 @@ def run_plmc(alignment, couplings_file, param_file=None,
 
     t0 = time.time()
     if engine is None:
+        ndev = _resolve_num_gpus(num_gpus, cpu, ali.n_valid, L, q, max_iter)
+        if ndev > 1:
+            from . import launcher
+            return launcher.run_plmc_multi_gpu(
+                ndev, return_run=return_run,
+                kwargs=dict(alignment=alignment, couplings_file=couplings_file, param_file=param_file,
+                            focus_seq=focus_seq, alphabet=alphabet, theta=theta, scale=scale,
+                            ignore_gaps=ignore_gaps, iterations=iterations, lambda_h=lambda_h, lambda_J=lambda_J,
+                            lambda_g=lambda_g, epsilon=epsilon, history=history,
+                            store_inverse_weights=store_inverse_weights, precision=precision))
         engine = _default_engine()
     rank = getattr(engine, "rank", 0)
     run.timings["engine_init_s"] = time.time() - t0
@@ -214,8 +263,9 @@ def run_plmc(alignment, couplings_file, param_file=None,
 
     # (a) PLM inference
     t0 = time.time()
+    extra = {} if precision is None else {"precision": precision}
     problem = engine.plm_problem(ali.codes, weights.astype(np.float32), q, ali.gap_code, lambda_h, lambda_J,
-                                 m=history)
+                                 m=history, **extra)
     run.timings["problem_setup_s"] = time.time() - t0
     try:
         t0 = time.time()
@@ -250,20 +300,27 @@ def run_plmc(alignment, couplings_file, param_file=None,
     J = x[L * q:].reshape(L * (L - 1) // 2, q, q)
 
     t0 = time.time()
+    write_error = None
     if rank == 0:
-        run.cn = model_io.write_ec_file(couplings_file, fn, L, ali.index_list, ali.target_seq)
-        if param_file is not None:
-            w_all = np.zeros(ali.n_total, dtype=np.float32)
-            # golden plmc run stores the integer neighbour counts (0 on invalid rows); newer plmc
-            # versions may store 1/n -- nothing in the reference reads this field numerically
-            w_all[ali.valid] = (weights if store_inverse_weights else counts).astype(np.float32)
-            model_io.write_model_file(
-                param_file, L, q, ali.n_valid, ali.n_total - ali.n_valid, int(res.iterations),
-                1.0 - theta, lambda_h, lambda_J, 0.0, n_eff, ali.model_alphabet, w_all,
-                ali.target_seq, ali.index_list, fi, h, fij, J)
-    coll = getattr(engine, "coll", None)
-    if coll is not None:
-        coll.barrier()          # multi-GPU: every rank returns only after rank 0 has written the files
+        try:
+            run.cn = model_io.write_ec_file(couplings_file, fn, L, ali.index_list, ali.target_seq)
+            if param_file is not None:
+                w_all = np.zeros(ali.n_total, dtype=np.float32)
+                # golden plmc run stores the integer neighbour counts (0 on invalid rows); newer plmc
+                # versions may store 1/n -- nothing in the reference reads this field numerically
+                w_all[ali.valid] = (weights if store_inverse_weights else counts).astype(np.float32)
+                model_io.write_model_file(
+                    param_file, L, q, ali.n_valid, ali.n_total - ali.n_valid, int(res.iterations),
+                    1.0 - theta, lambda_h, lambda_J, 0.0, n_eff, ali.model_alphabet, w_all,
+                    ali.target_seq, ali.index_list, fi, h, fij, J)
+        except Exception as e:          # agreed across ranks below: nobody is left waiting in a collective
+            write_error = e
+    agree = getattr(engine, "agree_any", None)
+    failed = agree(write_error is not None) if agree is not None else (write_error is not None)
+    if failed:
+        if write_error is not None:
+            raise write_error
+        raise ResourceError("rank 0 failed to write the plmc output files")
     run.timings["write_files_s"] = time.time() - t0
     run.log = "\n".join(log) + "\n"
     run.timings["total_s"] = time.time() - t_start

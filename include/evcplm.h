@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define EVCPLM_ABI_VERSION 1
+#define EVCPLM_ABI_VERSION 2
 
 typedef struct evc_plm evc_plm_t;
 
@@ -72,6 +72,23 @@ int evc_hamming_count_tiles(const uint32_t *d_planes, int64_t N, int32_t L, int3
                             int64_t tile_begin, int64_t tile_end, int32_t *d_counts /* += */,
                             void *stream);
 
+/* f3 twin of identities_to_seq (evcouplings/align/alignment.py:1156-1189): d_out[n] = #{k : codes[n,k] == seq[k]} */
+int evc_identities_to_seq(const uint8_t *d_codes /* N x L */, const uint8_t *d_seq /* L */, int64_t N, int32_t L,
+                          int32_t *d_out, void *stream);
+
+/* ---- f4: compiled A2M / FASTA ingest (host code) ---------------------------------------------------------
+ * Replaces the reference's in-tree text readers (evcouplings/align/alignment.py:42-74 read_fasta, 410-443
+ * sequences_to_matrix, 479-495 map_matrix) and plmc's own parser (8a row a4).  Return 0 ok, 1 I/O or argument
+ * error, 2 malformed alignment (no sequences / zero length / ragged rows); message in evc_last_error().
+ *   evc_a2m_scan:   number of records, common row width, bytes for the NUL-separated record ids
+ *   evc_a2m_read:   raw characters (n_rows x width, as in the file: case and '.' preserved) and the ids
+ *   evc_msa_encode: codes_out[v][k] = lut[raw[row_v][cols[k]]] for the VALID rows only (a row is valid iff no
+ *                   character of the whole row maps to 255), valid_out[r] in {0,1}, *n_valid_out rows written */
+int evc_a2m_scan(const char *path, int64_t *n_rows, int64_t *width, int64_t *ids_bytes);
+int evc_a2m_read(const char *path, int64_t n_rows, int64_t width, uint8_t *raw, char *ids, int64_t ids_bytes);
+int evc_msa_encode(const uint8_t *raw, int64_t n_rows, int64_t width, const uint8_t *lut, const int64_t *cols,
+                   int64_t n_cols, uint8_t *valid_out, uint8_t *codes_out, int64_t *n_valid_out);
+
 /* ---- (a) PLM objective + gradient -----------------------------------------
  * Replaces plmc's negative-log-posterior evaluation (the inner loop of its
  * L-BFGS).
@@ -97,6 +114,14 @@ int evc_plm_set_backward(evc_plm_t *h, int32_t mode);
  * matrix in HBM; protein alphabets, falls back to 1 otherwise).  Modes 1 and 2 imply the tensor-core backward. */
 int evc_plm_set_forward(evc_plm_t *h, int32_t mode);
 
+/* Arithmetic of the tensor-core products (SURVEY.md 8b `precision`; BASELINE configs[4] "bf16 tiles / fp32
+ * parameters"): 0 (default) = fp32-equivalent: the real-valued operand (couplings forward, residuals backward)
+ * enters as TWO bf16 terms hi + lo (16 mantissa bits), two tcgen05.mma per K slice; 1 = bf16 tiles: ONE bf16
+ * term, one tcgen05.mma per K slice (half the tensor-core work).  Parameters, accumulation (TMEM, K chunks
+ * promoted with fp32 round-to-nearest adds), softmax and the optimiser stay fp32 in both modes.  No effect on
+ * the gather kernels.  May be changed between evaluations. */
+int evc_plm_set_precision(evc_plm_t *h, int32_t mode);
+
 /* Per-stage device timing of the LAST evc_plm_eval_data call (CUDA events recorded on the stream the
  * kernels were launched on): ms_out[5] = {expand (+ clear), forward (gather kernel or logits GEMM),
  * softmax kernel (0 on the gather forward), backward kernel, finalize}.
@@ -119,6 +144,62 @@ int evc_plm_eval_host(evc_plm_t *h, const float *x, float *g, double *fx_out,
  * sum_s w_s [s_i=a] and sum_s w_s [s_i=a][s_j=b]; the host normalises
  * (N_eff, or per-site / per-pair non-gap weight under ignore_gaps). */
 int evc_plm_weighted_counts(evc_plm_t *h, float *d_fi_counts, float *d_fij_counts, void *stream);
+
+/* ---- a8: the whole L-BFGS fit on the device (replaces plmc's libLBFGS loop; iteration cap = plmc `-m`,
+ * evcouplings/couplings/tools.py:226-228) ---------------------------------------------------------------
+ * Minimises  -sum_s w_s sum_i log P(s_i | s_-i) + lambda_h |h|^2 + lambda_J |J|^2  from the start point in d_x
+ * (device, n floats; overwritten with the result).  All vectors live in the handle; the host sees six doubles
+ * per objective evaluation.  Status codes carry libLBFGS's names (plmc prints them after
+ * "Gradient optimization:", parsed at tools.py:57). */
+enum {
+    EVC_LBFGS_SUCCESS = 0,
+    EVC_LBFGS_ALREADY_MINIMIZED = 2,
+    EVC_LBFGSERR_CANCELED = -1021,
+    EVC_LBFGSERR_INVALIDPARAMETERS = -1000,
+    EVC_LBFGSERR_MINIMUMSTEP = -1001,
+    EVC_LBFGSERR_MAXIMUMSTEP = -1002,
+    EVC_LBFGSERR_MAXIMUMLINESEARCH = -1003,
+    EVC_LBFGSERR_MAXIMUMITERATION = -1004,
+    EVC_LBFGSERR_WIDTHTOOSMALL = -1005,
+    EVC_LBFGSERR_ROUNDING_ERROR = -1006,
+    EVC_LBFGSERR_INCREASEGRADIENT = -1007
+};
+typedef struct {
+    int32_t max_iterations;      /* 0 = until convergence                                             */
+    int32_t m;                   /* correction pairs kept (1..32)                                      */
+    float epsilon;               /* stop when |g| / max(1, |x|) <= epsilon                             */
+    float lambda_h, lambda_J;
+    int32_t max_linesearch;
+    double min_step, max_step, ftol, gtol, xtol;
+    int32_t precision_schedule;  /* 0: keep the handle's precision; 1: bf16 tiles until
+                                    |g|/max(1,|x|) <= switch_factor * epsilon (or the line search fails),
+                                    then fp32-equivalent products to the end                            */
+    float switch_factor;
+} evc_fit_params_t;
+typedef struct {
+    int32_t status;              /* EVC_LBFGS*                                                          */
+    int32_t iterations;
+    int32_t evaluations;
+    int32_t switched_at;         /* iteration at which precision_schedule 1 left the bf16 mode, or -1   */
+    double fx, negloglk;
+    double seconds;
+} evc_fit_result_t;
+/* Sum d_buf[0..count) over all ranks in place, asynchronously on `stream` (NCCL all-reduce in the Python host).
+ * The buffer is the gradient followed by 4 floats that carry -loglk as exact fixed-point limbs: ONE collective
+ * per evaluation.  NULL = single rank.  Return non-zero to abort. */
+typedef int (*evc_allreduce_cb)(void *user, float *d_buf, int64_t count, void *stream);
+/* Called once per iteration (the row of plmc's iteration table, tools.py:59-83); non-zero return cancels. */
+typedef int (*evc_progress_cb)(void *user, int32_t iteration, double fx, double xnorm, double gnorm, double step,
+                               int32_t linesearch_evals, double negloglk, double hnorm, double enorm);
+void evc_fit_default_params(evc_fit_params_t *p);
+int evc_plm_fit(evc_plm_t *h, float *d_x, const evc_fit_params_t *params, evc_allreduce_cb allreduce,
+                void *allreduce_user, evc_progress_cb progress, void *progress_user, evc_fit_result_t *result,
+                void *stream);
+
+/* -loglk <-> 4 floats appended to the gradient (three exact fixed-point limbs, resolution 2^-16, |fx| < 1.3e11, up to 64 ranks):
+ * a data-parallel evaluation then needs ONE all-reduce of n + 4 floats (SURVEY.md 8e `[fx, g]`). */
+int evc_plm_pack_fx(const double *d_fx, float *d_limbs, void *stream);
+int evc_plm_unpack_fx(const float *d_limbs, double *d_fx, void *stream);
 
 /* ---- a8: on-device L-BFGS vector algebra ----------------------------------
  * All scalars stay on the device (double); the host reads back only what the

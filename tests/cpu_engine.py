@@ -109,3 +109,62 @@ class OracleEngine(object):
 
     def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6):
         return OracleProblem(codes, weights, q, gap_code, lambda_h, lambda_J, m, self.precision)
+
+
+class ShardedOracleProblem(OracleProblem):
+    """Data-parallel twin of the CUDA problem for the gloo tests of the multi-rank plumbing: this rank's
+    contiguous block of sequences, ONE all-reduce of [g, -loglk] per evaluation, regulariser after."""
+
+    def __init__(self, engine, *a, **k):
+        super().__init__(*a, **k)
+        from evcouplings_b200.dist import shard_bounds
+        self.engine = engine
+        lo, hi = shard_bounds(self.codes.shape[0], engine.world, engine.rank)
+        self.c_loc, self.w_loc = self.codes[lo:hi], self.w[lo:hi]
+
+    def evaluate(self, x):
+        import torch
+        nll, g, _ = co.plm_eval(self.c_loc, self.w_loc, x, self.q, 0.0, 0.0, precision="f64")
+        packed = torch.from_numpy(np.concatenate([g, [nll]]))
+        self.engine.coll.all_reduce_sum(packed)
+        packed = packed.numpy()
+        nh = self.L * self.q
+        lam = np.concatenate([np.full(nh, self.lambda_h), np.full(self.n - nh, self.lambda_J)])
+        self.g[:] = packed[:-1] + 2 * lam * x
+        self.last_negloglk = float(packed[-1])
+        self.evaluations += 1
+        return self.last_negloglk + float((lam * x * x).sum())
+
+    def weighted_counts(self):
+        import torch
+        X = po.one_hot(self.c_loc, self.q)
+        Xw = X * self.w_loc[:, None, None]
+        fi = Xw.sum(axis=0)
+        F = np.einsum("nia,njb->ijab", Xw, X, optimize=True)
+        iu, ju = np.triu_indices(self.L, 1)
+        tf, tF = torch.from_numpy(np.ascontiguousarray(fi)), torch.from_numpy(np.ascontiguousarray(F[iu, ju]))
+        self.engine.coll.all_reduce_sum(tf)
+        self.engine.coll.all_reduce_sum(tF)
+        return tf.numpy(), tF.numpy()
+
+
+class ShardedOracleEngine(object):
+    """OracleEngine as one rank of an initialised torch.distributed (gloo) group."""
+
+    def __init__(self, precision="f64"):
+        from evcouplings_b200.dist import Collective
+        self.coll = Collective()
+        self.rank, self.world = self.coll.rank, self.coll.world
+        self.precision = precision
+
+    def hamming_counts(self, codes, min_identical):
+        return co.hamming_counts(codes, min_identical)
+
+    def plm_problem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m=6):
+        return ShardedOracleProblem(self, codes, weights, q, gap_code, lambda_h, lambda_J, m, self.precision)
+
+    def agree_any(self, flag):
+        import torch
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32)
+        self.coll.all_reduce_max(t)
+        return bool(int(t.item()))

@@ -1,5 +1,6 @@
 """
-Import the (Python) reference from /root/reference inside this container.
+Import the (Python) reference: from /root/reference inside this container, or from the git-ignored install
+baseline/_ref (scripts/install_reference.sh), which travels to the GPU box with gpurun.
 
 The reference's optional plotting / batch dependencies are absent here
 (ruamel.yaml, matplotlib, seaborn, bokeh, billiard, Bio); none of them is on
@@ -16,7 +17,9 @@ import types
 import warnings
 from unittest import mock
 
-REFERENCE_ROOT = "/root/reference"
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_CANDIDATES = ("/root/reference", os.path.join(_REPO, "baseline", "_ref"))
+REFERENCE_ROOT = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "evcouplings"))), _CANDIDATES[0])
 _STUB_ROOTS = ("matplotlib", "seaborn", "bokeh", "billiard", "Bio", "mpl_toolkits")
 
 
@@ -85,7 +88,7 @@ def install():
     if _installed:
         return
     if not available():
-        raise RuntimeError("/root/reference is not present")
+        raise RuntimeError("the reference is present neither at /root/reference nor in baseline/_ref")
     warnings.filterwarnings("ignore", category=SyntaxWarning)
     _install_ruamel_shim()
     if not any(isinstance(f, _StubFinder) for f in sys.meta_path):

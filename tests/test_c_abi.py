@@ -22,7 +22,7 @@ def test_header_binding_and_library_agree():
     for name in sorted(declared):
         assert hasattr(lib, name), "libevcplm.so does not export " + name
     bound = _lib.load()
-    assert bound.evc_abi_version() == _lib.ABI_VERSION == 1
+    assert bound.evc_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_reports_errors_without_device():
@@ -35,3 +35,43 @@ def test_library_reports_errors_without_device():
     assert rc != 0 and b"null handle" in lib.evc_last_error()
     rc = lib.evc_hamming_counts(None, 0, 0, 0, 0, None)
     assert rc != 0 and lib.evc_last_error()
+
+
+def test_create_validates_code_range_before_touching_a_device():
+    """a code >= q (q + 1 with the ignored gap) must be rejected, not used as a row index."""
+    import numpy as np
+    from evcouplings_b200 import _lib
+    lib = _lib.load()
+    w = np.ones(4, dtype=np.float32)
+    h = ctypes.c_void_p()
+    for q, gap, bad in ((21, -1, 21), (20, 20, 21), (4, -1, 200)):
+        codes = np.zeros((4, 3), dtype=np.uint8)
+        codes[2, 1] = bad
+        rc = lib.evc_plm_create(ctypes.byref(h), codes.ctypes.data_as(ctypes.c_void_p), 4, 3, q, gap,
+                                w.ctypes.data_as(ctypes.c_void_p), 0)
+        assert rc != 0 and b"out of range" in lib.evc_last_error(), lib.evc_last_error()
+
+
+def test_compiled_a2m_reader_matches_python_reader(tmp_path):
+    """f4: csrc/a2m_reader.cu against the pure-Python line loop: wrapped records, CRLF, blank lines, text before the
+    first header, lower-case inserts and '.'; error classes for empty / ragged / zero-length input."""
+    import numpy as np
+    import pytest
+    from evcouplings_b200 import msa
+    text = ("junk before the first record\n>seqA/5-14 some description\r\nACDEF\r\nghik.\n\n>seqB\n"
+            "AC-EFGH\nIK.\n>seqC\nacdefGHIK-\n")
+    p = tmp_path / "a.a2m"
+    p.write_bytes(text.encode())
+    ids, raw = msa.read_fasta_matrix(str(p))
+    ids_py, raw_py = msa.read_fasta_matrix_py(str(p))
+    assert ids == ids_py == ["seqA/5-14 some description", "seqB", "seqC"]
+    assert raw.shape == (3, 10) and np.array_equal(raw, raw_py)
+    ali = msa.load_alignment(str(p), focus="seqA")
+    assert ali.region_start == 5 and ali.target_seq == "ACDEF" and ali.codes.shape == (3, 5)
+    for bad, msg in ((b"", "no sequences"), (b">a\nAC\n>b\nACD\n", "ragged"), (b">a\n>b\n", "zero-length")):
+        q = tmp_path / "bad.a2m"
+        q.write_bytes(bad)
+        with pytest.raises(msa.AlignmentError, match=msg):
+            msa.read_fasta_matrix(str(q))
+        with pytest.raises(msa.AlignmentError, match=msg):
+            msa.read_fasta_matrix_py(str(q))

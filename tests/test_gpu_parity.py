@@ -308,6 +308,7 @@ def test_lbfgs_vector_algebra(engine):
     import torch
     codes = synthetic.synthetic_msa_codes(64, 9, 2)
     prob = engine.plm_problem(codes, np.ones(64, dtype=np.float32), 21, -1, 0.01, 1.0, m=4)
+    prob._ensure_python_space()       # vectors of the Python driver (the default fit runs inside libevcplm)
     n, m = prob.n, 4
     rng = np.random.default_rng(0)
     a, b = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
@@ -462,6 +463,136 @@ def test_full_size_properties(engine):
 
 
 # ------------------------------------------------------------------------------------------------
+# full BASELINE sizes of configs 4 (per-GPU share, L=500) and 5 (N=100k, L=800): tile scheduler, K-chunk promotion
+# over 100k sequences, L*q = 16,800 -- against the float64 oracle through the shard-additivity identity
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,L,precision", [(62500, 500, "fp32"), (100000, 800, "fp32"), (100000, 800, "bf16")])
+def test_full_size_config4_config5_shapes(engine, N, L, precision):
+    import torch
+    q, ns = 21, 2000
+    codes = synthetic.synthetic_msa_codes(N, L, 4 if L == 500 else 5)
+    rng = np.random.default_rng(L)
+    w = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    n = L * q + L * (L - 1) // 2 * q * q
+    x = rng.normal(0, 0.02, n).astype(np.float32)
+    full = engine.plm_problem(codes, w, q, -1, 0.0, 0.0, precision=precision)
+    full.set_x(x)
+    f_full = full.evaluate(full.x)
+    g_full = full.g.clone()
+    full.close()
+    rest = engine.plm_problem(codes[ns:], w[ns:], q, -1, 0.0, 0.0, precision=precision)
+    rest.set_x(x)
+    f_rest = rest.evaluate(rest.x)
+    g_part = (g_full - rest.g).cpu().numpy().astype(np.float64)      # = gradient of the first ns sequences
+    gnorm = float(g_full.double().norm())
+    rest.close()
+    del g_full
+    torch.cuda.empty_cache()
+    fo, go, _ = co.plm_eval(codes[:ns], w[:ns].astype(np.float64), x.astype(np.float64), q, 0.0, 0.0, "f64")
+    err = np.linalg.norm(g_part - go)
+    print("N=%d L=%d %s: |g_full - g_rest - g_oracle(first %d)| / |g_full| = %.3e; fx identity rel %.3e"
+          % (N, L, precision, ns, err / gnorm, abs((f_full - f_rest) - fo) / abs(f_full)))
+    # stated tolerances.  fp32-equivalent products: 2e-5 of |g_full| (two fp32 GPU gradients are subtracted);
+    # bf16 tiles (BASELINE configs[4] mode): 8-bit mantissa products => 5e-3 of |g_full|, fx 1e-3 of the slice
+    if precision == "fp32":
+        assert err <= 2e-5 * gnorm
+        assert abs((f_full - f_rest) - fo) <= 2e-6 * abs(f_full)
+    else:
+        assert err <= 5e-3 * gnorm
+        assert abs((f_full - f_rest) - fo) <= 1e-3 * abs(fo) + 2e-6 * abs(f_full)
+
+
+# ------------------------------------------------------------------------------------------------
+# precision mode 1 ("bf16 tiles / fp32 parameters", BASELINE configs[4]; SURVEY 8b `precision`)
+# ------------------------------------------------------------------------------------------------
+def test_precision_bf16_tiles_vs_fp32_mode(engine):
+    """One bf16 product per term instead of the hi+lo pair.  Stated tolerance against the fp32-equivalent run of
+    the SAME kernels at the same point: gradient rel. L2 <= 1e-2, objective rel. <= 1e-3 (bf16 keeps 8 mantissa
+    bits of each coupling / residual; the one-hot operand stays exact; accumulation stays fp32)."""
+    N, L, q = 6000, 120, 21
+    codes = synthetic.synthetic_msa_codes(N, L, 11)
+    rng = np.random.default_rng(11)
+    w = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    n = L * q + L * (L - 1) // 2 * q * q
+    x = rng.normal(0, 0.05, n).astype(np.float32)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        p = engine.plm_problem(codes, w, q, -1, 0.01, 5.0, precision=prec)
+        p.set_x(x)
+        res[prec] = (p.evaluate(p.x), p.g.cpu().numpy().astype(np.float64))
+        p.close()
+    fo, go, _ = co.plm_eval(codes, w.astype(np.float64), x.astype(np.float64), q, 0.01, 5.0, "f64")
+    e32 = np.linalg.norm(res["fp32"][1] - go) / np.linalg.norm(go)
+    e16 = np.linalg.norm(res["bf16"][1] - go) / np.linalg.norm(go)
+    f16 = abs(res["bf16"][0] - fo) / abs(fo)
+    print("gradient rel L2 vs float64 oracle: fp32 mode %.2e, bf16 tiles %.2e; fx rel (bf16) %.2e" % (e32, e16, f16))
+    assert e32 <= 5e-6
+    assert e16 <= 1e-2 and f16 <= 1e-3
+    assert np.linalg.norm(res["bf16"][1] - res["fp32"][1]) <= 1e-2 * np.linalg.norm(res["fp32"][1])
+
+
+def test_precision_schedule_auto_reaches_the_fp32_optimum(engine, tmp_path):
+    """precision="auto": bf16 tiles until |g|/|x| < 10 eps, then fp32-equivalent products to convergence.  The fitted
+    EC scores must agree with the pure fp32 run within the north-star tolerance (rms <= 1e-4)."""
+    N, L = 400, 40
+    codes = synthetic.synthetic_msa_codes(N, L, 12)
+    a2m = tmp_path / "p.a2m"
+    synthetic.write_a2m(str(a2m), codes)
+    lam_J = 0.01 * 20 * (L - 1)
+    out = {}
+    for prec in ("fp32", "auto", "bf16"):
+        res, run = tools.run_plmc(str(a2m), str(tmp_path / (prec + "_ECs.txt")), str(tmp_path / (prec + ".model")),
+                                  focus_seq="seq0", theta=0.8, iterations=2000, lambda_h=0.01, lambda_J=lam_J,
+                                  engine=engine, return_run=True, epsilon=1e-5, precision=prec)
+        out[prec] = (np.loadtxt(str(tmp_path / (prec + "_ECs.txt")), usecols=5), res, run)
+        print(prec, res.optimization_status, run.lbfgs.iterations, run.lbfgs.evaluations)
+    rms_auto = np.sqrt(np.mean((out["auto"][0] - out["fp32"][0]) ** 2))
+    rms_bf16 = np.sqrt(np.mean((out["bf16"][0] - out["fp32"][0]) ** 2))
+    print("EC rms vs the fp32 run: auto %.2e, bf16-only %.2e" % (rms_auto, rms_bf16))
+    assert out["fp32"][1].optimization_status == "LBFGS_SUCCESS"
+    assert out["auto"][1].optimization_status == "LBFGS_SUCCESS"
+    assert rms_auto <= 1e-4
+    assert rms_bf16 <= 2e-2          # bf16 tiles alone: stated (looser) tolerance; may stop on the line search
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: the device-resident L-BFGS (evc_plm_fit) against the Python driver of the same algorithm
+# ------------------------------------------------------------------------------------------------
+def test_device_fit_matches_python_driver(engine):
+    N, L, q = 1200, 30, 21
+    codes = synthetic.synthetic_msa_codes(N, L, 13)
+    w = (1.0 / co.hamming_counts(codes, msa.identity_threshold_count(0.8, L))).astype(np.float32)
+    params = lbfgs.default_params(max_iterations=25, epsilon=1e-9, m=6)
+    traces = {}
+    xs = {}
+    for driver in ("device", "python"):
+        p = engine.plm_problem(codes, w, q, -1, 0.01, 0.01 * 20 * (L - 1))
+        tr = []
+        res = p.fit(np.zeros(p.n, dtype=np.float32), params, progress=lambda k, fx, xn, gn, st, nls: tr.append((fx, gn, st, nls)) and False,
+                    driver=driver)
+        traces[driver] = (np.array(tr), res)
+        xs[driver] = p.get_x()
+        p.close()
+    td, tp = traces["device"][0], traces["python"][0]
+    assert traces["device"][1].status == traces["python"][1].status == "LBFGSERR_MAXIMUMITERATION"
+    assert len(td) == len(tp) == 25
+    assert np.abs(td[:, 0] - tp[:, 0]).max() <= 1e-6 * np.abs(tp[:, 0]).max()       # fx per iteration
+    assert np.array_equal(td[:, 3], tp[:, 3])                                         # line-search evaluations
+    assert np.abs(xs["device"] - xs["python"]).max() <= 1e-4
+    assert traces["device"][1].evaluations == traces["python"][1].evaluations
+
+
+def test_create_rejects_out_of_range_codes(lib):
+    codes = synthetic.synthetic_msa_codes(64, 8, 1)
+    codes[5, 3] = 21                                   # q = 21 without an ignored gap: valid codes are 0..20
+    w = np.ones(64, dtype=np.float32)
+    h = ctypes.c_void_p()
+    rc = lib.evc_plm_create(ctypes.byref(h), codes.ctypes.data_as(ctypes.c_void_p), 64, 8, 21, -1,
+                            w.ctypes.data_as(ctypes.c_void_p), 0)
+    assert rc != 0 and b"out of range" in lib.evc_last_error()
+
+
+# ------------------------------------------------------------------------------------------------
 # 8(f3): GPU drop-ins of the reference's in-tree numba twins
 # ------------------------------------------------------------------------------------------------
 def test_intree_twin_dropins_vs_reference_outputs(engine, golden_dir):
@@ -483,6 +614,39 @@ def test_intree_twin_dropins_vs_reference_outputs(engine, golden_dir):
         assert np.abs(fij[iu, ju] - d[name + "_fij_tri"]).max() < 2e-6
         assert np.abs(fij[ju, iu] - d[name + "_fij_tri"].transpose(0, 2, 1)).max() < 2e-6
         assert np.allclose(fij[3, 3][np.arange(21), np.arange(21)], fi[3])
+
+
+def test_identities_to_seq_and_set_weights_vs_reference_class(engine):
+    """f3: identities_to_seq (alignment.py:1156-1189) and Alignment.set_weights (:899-930) drop-ins.  When the
+    reference is importable (baseline/_ref on the GPU box) the reference's own numba function and Alignment class
+    are the comparison; the definition (row-wise equality count) always is."""
+    from evcouplings_b200 import alignment as ga
+    rng = np.random.default_rng(5)
+    for N, L in ((1, 1), (257, 33), (5000, 301)):
+        m = rng.integers(0, 21, size=(N, L))
+        s = m[rng.integers(0, N)].copy()
+        got = ga.identities_to_seq(s, m, engine=engine)
+        assert got.dtype == np.float64 and np.array_equal(got, (m == s[None, :]).sum(axis=1).astype(np.float64))
+    with pytest.raises(ValueError):
+        ga.frequencies(np.full((4, 3), 21), np.ones(4), 21, engine=engine)        # symbol out of range
+    import ref_harness
+    if not ref_harness.available():
+        return
+    ref_harness.install()
+    from evcouplings.align.alignment import Alignment, identities_to_seq as ref_ids
+    codes = synthetic.synthetic_msa_codes(300, 25, 9)
+    seqs = ["".join(synthetic.ALPHABET[c] for c in row) for row in codes]
+    ali_ref = Alignment.from_dict({"s%d" % k: v for k, v in enumerate(seqs)})
+    ali_gpu = Alignment.from_dict({"s%d" % k: v for k, v in enumerate(seqs)})
+    f_before = ali_gpu.frequencies.copy()                  # cached, unweighted
+    ali_ref.set_weights(0.8)
+    ga.set_weights(ali_gpu, 0.8, engine=engine)
+    assert np.array_equal(ali_gpu.num_cluster_members, ali_ref.num_cluster_members)
+    assert np.array_equal(ali_gpu.weights, ali_ref.weights)
+    # the drop-in resets the cached frequencies like the reference does: the next access is weighted
+    assert np.allclose(ali_gpu.frequencies, ali_ref.frequencies) and not np.allclose(ali_gpu.frequencies, f_before)
+    mapped = ali_ref.matrix_mapped
+    assert np.array_equal(ga.identities_to_seq(mapped[0], mapped, engine=engine), ref_ids(mapped[0], mapped))
 
 
 # ------------------------------------------------------------------------------------------------
