@@ -195,13 +195,28 @@ def run_reference(args):
 
 
 def _nccl_env():
-    # NCCL's rank / topology lines go to stderr so that the driver can count ranks and stdout stays one JSON line
-    if "EVC_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["EVC_NCCL_DEBUG"]
-    else:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    """NCCL's INIT lines (rank / nranks / topology) are wanted on STDERR so that the driver can count ranks, and
+    stdout must stay ONE JSON line (NCCL prints its version banner and, without a debug file, everything to stdout).
+    NCCL therefore logs into a per-rank temporary file that _nccl_log_to_stderr() copies to stderr at the end."""
+    os.environ["NCCL_DEBUG"] = os.environ.get("EVC_NCCL_DEBUG", "INFO")
+    os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("EVC_NCCL_DEBUG_SUBSYS", "INIT")
+    d = tempfile.mkdtemp(prefix="evc_nccl_")
+    os.environ["NCCL_DEBUG_FILE"] = os.path.join(d, "nccl.%h.%p.log")
+    return d
+
+
+def _nccl_log_to_stderr(d):
+    try:
+        for name in sorted(os.listdir(d)):
+            with open(os.path.join(d, name)) as f:
+                for ln in f:
+                    if "NCCL" in ln:
+                        sys.stderr.write(ln)
+            os.unlink(os.path.join(d, name))
+        os.rmdir(d)
+        sys.stderr.flush()
+    except Exception:
+        pass
 
 
 def hamming_subrecord(engine, peaks, steps=3):
@@ -264,11 +279,13 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    _nccl_env()
+    nccl_dir = _nccl_env()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        sys.stderr.write("[bench] rank %d / %d on cuda:%d, backend nccl %s\n"
+                         % (rank, world, local_rank, ".".join(str(v) for v in torch.cuda.nccl.version())))
     else:
         torch.cuda.set_device(0)
     from evcouplings_b200 import msa
@@ -307,6 +324,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = engine.kernel_launches
+    prob.time_collective, prob.collective_events = world > 1, []
     stage = np.zeros(5, dtype=np.float32)
     stage_sum = np.zeros(5, dtype=np.float64)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -330,7 +348,21 @@ def run_b200(args):
 
     # ---- rank consistency: after the all-reduce every rank must hold the same objective and gradient ----
     consistency = None
+    comm = None
+    prob.time_collective = False
     if world > 1:
+        # where the multi-GPU step goes: compute per rank (sum of the stage timers) and the collective as THIS rank
+        # sees it (its duration includes waiting for the slowest rank)
+        coll_ms = float(np.mean([a.elapsed_time(b) for a, b in prob.collective_events])) if prob.collective_events else 0.0
+        mine = torch.tensor([float(stage_ms.sum()), coll_ms], dtype=torch.float64, device=engine.device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        comp = [float(t_[0]) for t_ in allr]
+        coll = [float(t_[1]) for t_ in allr]
+        comm = {"compute_ms_per_rank": comp, "collective_ms_per_rank_incl_wait": coll,
+                "collective_ms_min_over_ranks": min(coll),
+                "note": "one all-reduce of %d floats per step; the minimum over ranks of the collective's duration is the "
+                        "best estimate of the transfer itself (the slowest rank does not wait)" % (n + 4)}
         chk = torch.stack([prob.fxbuf[0], prob.fxbuf[1], prob.g.double().sum(), prob.g.double().abs().sum()])
         gathered = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(gathered, chk)
@@ -440,6 +472,8 @@ def run_b200(args):
     }
     if consistency is not None:
         line["rank_consistency"] = consistency
+    if comm is not None:
+        line["communication"] = comm
 
     # ---- correctness of the timed path (every world size; the oracle is the checker only) ----
     if rank == 0:
@@ -503,10 +537,12 @@ def run_b200(args):
             line["hamming"]["unpruned"] = hamming_unpruned_ms()
         except Exception as e:
             line["hamming"] = {"error": "%s: %s" % (type(e).__name__, e)}
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    _nccl_log_to_stderr(nccl_dir)
+    if rank == 0:
+        print(json.dumps(line))
+        sys.stdout.flush()
 
 
 def ncu_traffic(kernel_name, precision):
@@ -598,7 +634,7 @@ def run_hamming(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
-    _nccl_env()
+    nccl_dir = _nccl_env()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -676,10 +712,11 @@ def run_hamming(args):
         line["cpu_baseline"] = {"value": rows * N / dt / 2, "unit": "pairs/s", "cores": host_threads(), "kind": "port",
                                 "sample": "%d of %d rows against all columns (%.1f s); unordered-pair equivalent" % (rows, N, dt)}
         line["parity_sample_rows_exact"] = bool(np.array_equal(got[:rows], ref))
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    _nccl_log_to_stderr(nccl_dir)
+    if rank == 0:
+        print(json.dumps(line))
 
 
 def main():

@@ -49,6 +49,7 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;        // 24576
 constexpr int TC_SMEM_LIMIT = 232448;                // 227 KB opt-in shared memory per CTA
 constexpr int TC_SMEM_HEAD = 2048;                   // 1 KB alignment slack + 1 KB of mbarriers / TMEM slot
 constexpr int TC_THREADS = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: epilogue (2 per TMEM lane quadrant)
+constexpr int TC_PAIR_DEFAULT = 0; // CTA-pair (cta_group::2) GEMM tiles: opt-in via EVC_TC_PAIR=1 until validated on hardware
 constexpr int TC_K_CHUNK = 32;   // k-blocks (of 64) accumulated in TMEM before promotion to an fp32 add
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -367,6 +368,233 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 192 tile per cluster of two CTAs (two SMs of one TPC).
+// Each CTA stages ITS 128 rows of the A operand(s) and ITS 96-row half of the B operand(s); the leader CTA
+// (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes
+// each CTA's 128 accumulator lanes.  Operand bytes per CTA per k-block: 44 KB (forward hi+lo), 40 KB (backward
+// hi+lo), 28 KB (bf16 tiles) instead of 56 / 64 / 40 KB for the same MMA work -- the 1-CTA kernel is fed at
+// 107 B/clk/SM in bf16-tiles mode and reaches only 54 % tensor-pipe activity (profiles/r2_ncu_full_bf16_tiles.csv).
+// Protocol (per stage s; all barriers live at the same shared-memory offsets in both CTAs):
+//   full[s]       leader only, 1 arrival + 2 x stage bytes: both CTAs' TMA loads complete_tx on the LEADER's barrier
+//                 (cp.async.bulk.tensor ... .cta_group::2 with the peer bit of the barrier address cleared)
+//   empty[s]      each CTA, 1 arrival: multicast tcgen05.commit of the leader's MMA thread
+//   acc_full[a]   each CTA, 1 arrival: multicast commit after the last MMA of a K chunk
+//   acc_empty[a]  leader only, 16 arrivals: the 8 epilogue warps of BOTH CTAs (remote mbarrier.arrive for the peer)
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address (pair leader)
+constexpr int TC_BN_HALF = TC_BN / 2;                 // 96 rows of B per CTA
+constexpr int TC_BH_BYTES = TC_BN_HALF * TC_BK * 2;   // 12288
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *tmap, int c0, int c1,
+                                                      uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1),
+        "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)      // arrives on `bar` of BOTH CTAs of the pair
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)    // arrive on the pair leader's copy of `bar`
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC_PEER_MASK)
+                 : "memory");
+}
+
+template <int SPLIT_A>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                    float *__restrict__ D, int64_t ldd, int m_tiles, int n_tiles, int num_kb, int k_chunk, int pgroup,
+                    int single, int n_stages)
+{
+    // operands: forward (SPLIT_A)  tmA0 = Wt_hi, tmA1 = Wt_lo (box 128 rows), tmB0 = X (box 96 rows), tmB1 unused
+    //           backward           tmA0 = Xt (box 128), tmA1 unused, tmB0 = Rt_hi, tmB1 = Rt_lo (box 96 rows)
+    // stage layout per CTA: [A0 16 KB][B0 12 KB][optional: A1 16 KB (forward) | B1 12 KB (backward)]
+    constexpr int BYTES2 = SPLIT_A ? TC_A_BYTES : TC_BH_BYTES;
+    const int stage_bytes = TC_A_BYTES + TC_BH_BYTES + (single ? 0 : BYTES2);
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem0 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                                             ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem0);
+    uint64_t *empty = full + TC_MAX_STAGES;
+    uint64_t *acc_full = empty + TC_MAX_STAGES;  // [2]
+    uint64_t *acc_empty = acc_full + 2;          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    unsigned char *smem = smem0 + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_pairs = (m_tiles + 1) >> 1;
+    const int total_tiles = m_pairs * n_tiles;
+    const int n_chunks = (num_kb + k_chunk - 1) / k_chunk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 16);        // 8 epilogue warps of each CTA of the pair
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // the peer's barriers are initialised before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own 96-row half of B; bytes land on the leader's barrier =====
+        const uint64_t keep = l2_policy_evict_last();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
+            int m_pair, n_tile;
+            decode_tile(tile, m_pairs, n_tiles, pgroup, m_pair, n_tile);
+            const int row_a = min(2 * m_pair + (int)rank, m_tiles - 1) * TC_BM;  // odd tile count: the peer recomputes the last tile, unstored
+            const int row_b = n_tile * TC_BN + (int)rank * TC_BN_HALF;
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait_bounded(&empty[s], ph ^ 1u);
+                unsigned char *st = smem + s * stage_bytes;
+                if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));
+                if (SPLIT_A) {
+                    tma_load_2d_pair_hint(st, &tmA0, kb * TC_BK, row_a, &full[s], keep);
+                    tma_load_2d_pair(st + TC_A_BYTES, &tmB0, kb * TC_BK, row_b, &full[s]);
+                    if (!single) tma_load_2d_pair_hint(st + TC_A_BYTES + TC_BH_BYTES, &tmA1, kb * TC_BK, row_a, &full[s], keep);
+                } else {
+                    tma_load_2d_pair(st, &tmA0, kb * TC_BK, row_a, &full[s]);
+                    tma_load_2d_pair(st + TC_A_BYTES, &tmB0, kb * TC_BK, row_b, &full[s]);
+                    if (!single) tma_load_2d_pair(st + TC_A_BYTES + TC_BH_BYTES, &tmB1, kb * TC_BK, row_b, &full[s]);
+                }
+                if (++s == n_stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ===== MMA issuer (leader CTA only): M = 256 across the pair =====
+        constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BM, TC_BN);
+        int s = 0, wl = 0;
+        uint32_t ph = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
+            for (int c = 0; c < n_chunks; c++, wl++) {
+                const int acc = wl & 1;
+                mbar_wait_bounded(&acc_empty[acc], (uint32_t)(((wl >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+                const int kb0 = c * k_chunk, kb1 = min(num_kb, kb0 + k_chunk);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait_bounded(&full[s], ph);
+                    tc_fence_after();
+                    unsigned char *st = smem + s * stage_bytes;
+                    const uint64_t d0 = make_desc_sw128(st);
+                    const uint64_t d1 = make_desc_sw128(st + TC_A_BYTES);
+                    const uint64_t d2 = make_desc_sw128(st + TC_A_BYTES + TC_BH_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                        umma_bf16_pair(tmem_d, d0 + koff, d1 + koff, idesc, first);
+                        if (!single) {
+                            if (SPLIT_A) umma_bf16_pair(tmem_d, d2 + koff, d1 + koff, idesc, 1u);     // A_lo * B
+                            else umma_bf16_pair(tmem_d, d0 + koff, d2 + koff, idesc, 1u);             // A * B_lo
+                        }
+                    }
+                    umma_commit_pair(&empty[s]);
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit_pair(&acc_full[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): this CTA's 128 accumulator lanes =====
+        const int quad = warp & 3;
+        const int ehalf = (warp - 4) >> 2;
+        constexpr int ECOLS = TC_BN / 2;
+        int wl = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
+            int m_pair, n_tile;
+            decode_tile(tile, m_pairs, n_tiles, pgroup, m_pair, n_tile);
+            const int m_tile = 2 * m_pair + (int)rank;
+            const int64_t row = (int64_t)m_tile * TC_BM + quad * 32 + lane;
+            float *out = D + row * ldd + (int64_t)n_tile * TC_BN + ehalf * ECOLS;
+            float accr[ECOLS];
+            for (int c = 0; c < n_chunks; c++, wl++) {
+                const int acc = wl & 1;
+                mbar_wait_bounded(&acc_full[acc], (uint32_t)((wl >> 1) & 1));
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                       (uint32_t)(acc * TC_BN + ehalf * ECOLS);
+#pragma unroll
+                for (int cc = 0; cc < ECOLS / 16; cc++) {
+                    uint32_t v[16];
+                    tmem_ld_cols<16>(taddr + cc * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        accr[cc * 16 + u] = (c == 0) ? __uint_as_float(v[u]) : accr[cc * 16 + u] + __uint_as_float(v[u]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&acc_empty[acc]);
+            }
+            if (m_tile < m_tiles) {
+#pragma unroll
+                for (int u = 0; u < ECOLS; u += 4)
+                    __stcs(reinterpret_cast<float4 *>(out + u), make_float4(accr[u], accr[u + 1], accr[u + 2], accr[u + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // the leader's MMAs read the peer's shared memory: leave together
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -797,7 +1025,18 @@ int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_l
     if (make_map(&m[0], d_xt, t.Mp, t.Kp, TC_BM)) return 1;
     if (make_map(&m[1], d_rt_hi, t.Np, t.Kp, TC_BN)) return 1;
     if (make_map(&m[2], d_rt_lo, t.Np, t.Kp, TC_BN)) return 1;
+    // CTA-pair kernel: each CTA loads a 96-row half of the B tile
+    if (make_map(&m[3], d_rt_hi, t.Np, t.Kp, TC_BN_HALF)) return 1;
+    if (make_map(&m[4], d_rt_lo, t.Np, t.Kp, TC_BN_HALF)) return 1;
     return 0;
+}
+
+// 1 = cta_group::2 tiles (256 x 192 per CTA pair), 0 = one CTA per 128 x 192 tile
+static int pair_mode()
+{
+    static int pm_env = -2;
+    const int e = env_int_once("EVC_TC_PAIR", &pm_env);
+    return e >= 0 ? e : TC_PAIR_DEFAULT;
 }
 
 int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, float *d_Gd, int single, cudaStream_t st)
@@ -811,6 +1050,19 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
     static int kc_env = -2;
     const int kc = env_int_once("EVC_KCHUNK", &kc_env);
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Np / TC_BN);
+    if (pair_mode()) {
+        const int pstage = TC_A_BYTES + TC_BH_BYTES + (single ? 0 : TC_BH_BYTES);
+        const int pstages = stages_for(pstage);
+        const size_t psmem = (size_t)pstages * pstage + TC_SMEM_HEAD;
+        EVC_CUDA(cudaFuncSetAttribute(tc_gemm_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        const int m_pairs = (m_tiles + 1) / 2;
+        const int pairs = std::min(sm_count_current() / 2, m_pairs * n_tiles);
+        tc_gemm_pair_kernel<0><<<2 * pairs, TC_THREADS, psmem, st>>>(m[0], m[0], m[3], m[4], d_Gd, t.Np, m_tiles, n_tiles,
+                                                                   (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK, m_pairs,
+                                                                   single, pstages);
+        EVC_KERNEL_CHECK();
+        return 0;
+    }
     const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
                                                                 (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK,
@@ -854,6 +1106,7 @@ int plm_tcf_make_maps(const PlmTcfGeom &t, void *d_wt_hi, void *d_wt_lo, void *d
     if (make_map(&m[0], d_wt_hi, t.Mp, t.Kw, TC_BM)) return 1;
     if (make_map(&m[1], d_wt_lo, t.Mp, t.Kw, TC_BM)) return 1;
     if (make_map(&m[2], d_x1h, t.Xrows, t.Kw, TC_BN)) return 1;
+    if (make_map(&m[3], d_x1h, t.Xrows, t.Kw, TC_BN_HALF)) return 1;      // CTA-pair kernel: 96-row half of the X tile
     return 0;
 }
 
@@ -892,8 +1145,22 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
     EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TC_SMEM_LIMIT));
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Ns / TC_BN);
-    const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     const int num_kb = (int)(t.Kw / TC_BK);
+    if (pair_mode()) {
+        const int pstage = TC_A_BYTES + TC_BH_BYTES + (single ? 0 : TC_A_BYTES);
+        const int pstages = stages_for(pstage);
+        const size_t psmem = (size_t)pstages * pstage + TC_SMEM_HEAD;
+        EVC_CUDA(cudaFuncSetAttribute(tc_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        const int m_pairs = (m_tiles + 1) / 2;
+        const int pairs = std::min(sm_count_current() / 2, m_pairs * n_tiles);
+        const int pgroup = std::max(1, std::min(m_pairs, (forward_mgroup(t, single, m_tiles) + 1) / 2));
+        tc_gemm_pair_kernel<1><<<2 * pairs, TC_THREADS, psmem, st>>>(m[0], m[1], m[3], m[3], d_zt, t.Ns, m_tiles, n_tiles,
+                                                                   num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK, pgroup,
+                                                                   single, pstages);
+        EVC_KERNEL_CHECK();
+        return 0;
+    }
+    const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
                                                                 num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK,
                                                                 forward_mgroup(t, single, m_tiles), single, n_stages);
@@ -989,6 +1256,6 @@ int plm_tcff_forward(const PlmGeom &g, const PlmTcffGeom &t, const void *maps, c
     return 0;
 }
 
-size_t plm_tc_map_bytes() { return 3 * sizeof(CUtensorMap); }
+size_t plm_tc_map_bytes() { return 6 * sizeof(CUtensorMap); }
 
 }  // namespace evc

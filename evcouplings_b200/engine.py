@@ -207,7 +207,15 @@ class CudaPlmProblem(object):
         if e.world > 1:
             limbs = self.g_packed[self.n:]
             _lib.check(self.lib.evc_plm_pack_fx(p(self.fxbuf), p(limbs), e.stream()), "evc_plm_pack_fx")
+            timed = getattr(self, "time_collective", False)
+            if timed:
+                torch = _torch()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
             e.all_reduce(self.g_packed)                     # ONE collective: [g, -loglk]
+            if timed:
+                ev[1].record()
+                self.collective_events.append(ev)
             _lib.check(self.lib.evc_plm_unpack_fx(p(limbs), p(self.fxbuf), e.stream()), "evc_plm_unpack_fx")
             e.kernel_launches += 2
         _lib.check(self.lib.evc_plm_add_regulariser(self.handle, p(x), p(self.g), p(self.fxbuf),

@@ -10,7 +10,7 @@ G=${1:-8}
 O=gpurun_out/r2m; mkdir -p $O
 PORT=$((29700 + G * 10))
 tr() { n=$1; shift; PORT=$((PORT+1)); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $n "$@"; }
-show() { python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[1], 'ms', round(d['ms_per_step'],4), 'value %.4g' % d['value'], d.get('rank_consistency'), d.get('accuracy'), d['roofline']['stage_ms'])" $1; }
+show() { python -c "import json,sys; d=json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1]); print(sys.argv[1], 'ms', round(d['ms_per_step'],4), 'value %.4g' % d['value'], d.get('rank_consistency'), d.get('communication'), d['roofline']['stage_ms'])" $1; }
 nvidia-smi --query-gpu=index,name --format=csv > $O/gpus_$G.txt
 if [ $G -eq 2 ]; then
   echo "== multi-GPU tests"
@@ -47,6 +47,8 @@ res, run = tools.run_plmc(a2m, "/tmp/cfg4_ECs.txt", "/tmp/cfg4.model", focus_seq
                           lambda_h=0.01, lambda_J=0.01 * 20 * (L - 1), cpu=8, return_run=True)
 wall = time.time() - t0
 fx = res.iteration_table["fx"].astype(float).values
+tt = res.iteration_table["time"].astype(float).values
+print("iteration-table time column (s):", list(tt[:4]), "...", list(tt[-2:]), flush=True)
 print(json.dumps(dict(wall_s=wall, timings=run.timings, iterations=len(fx), fx=list(fx[:3]) + list(fx[-2:]),
                       status=res.optimization_status, n_eff=res.effective_samples,
                       model_bytes=os.path.getsize("/tmp/cfg4.model"))), flush=True)
