@@ -550,10 +550,18 @@ def test_precision_schedule_auto_reaches_the_fp32_optimum(engine, tmp_path):
     rms_auto = np.sqrt(np.mean((out["auto"][0] - out["fp32"][0]) ** 2))
     rms_bf16 = np.sqrt(np.mean((out["bf16"][0] - out["fp32"][0]) ** 2))
     print("EC rms vs the fp32 run: auto %.2e, bf16-only %.2e" % (rms_auto, rms_bf16))
-    # at epsilon = 1e-5 the fp32 evaluation noise usually ends the run in the line search (LBFGSERR_ROUNDING_ERROR)
-    # just before the gradient criterion triggers; what is asserted is where the runs end up
-    cond = lambda r: float(r.iteration_table["cond"].astype(float).values[-1])
-    assert cond(out["fp32"][1]) < 1e-3 and cond(out["auto"][1]) < 1e-3
+    # at epsilon = 1e-5 the fp32 evaluation noise ends these runs in the line search (LBFGSERR_ROUNDING_ERROR: fx
+    # differences fall below 1e-7 * fx) before the gradient criterion triggers; what is asserted is WHERE they end up:
+    # against each other and against the float64 optimum of the same objective
+    ali = out["auto"][2].alignment
+    w = 1.0 / co.hamming_counts(ali.codes, msa.identity_threshold_count(0.8, L))
+    xo, _ = po.fit(ali.codes, w, 21, 0.01, lam_J, ali.gap_code, x0=tools.initial_point(
+        po.frequencies(ali.codes, w, 21, ali.gap_code)[0], w.sum(), L, 21).astype(np.float64), max_iter=4000,
+        objective_fn=lambda v: co.plm_eval(ali.codes, w, v, 21, 0.01, lam_J, "f64"))
+    cn_opt = po.cn_scores(xo[L * 21:].reshape(-1, 21, 21), L)
+    rms_opt = {k: float(np.sqrt(np.mean((out[k][0] - cn_opt) ** 2))) for k in out}
+    print("EC rms vs the float64 optimum:", rms_opt)
+    assert rms_opt["fp32"] <= 1e-4 and rms_opt["auto"] <= 1e-4
     assert rms_auto <= 1e-4          # measured 8e-6
     assert rms_bf16 <= 2e-3          # bf16 tiles alone: stated (looser) tolerance, measured 3.5e-4
 
