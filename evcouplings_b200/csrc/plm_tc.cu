@@ -50,6 +50,7 @@ constexpr int TC_SMEM_LIMIT = 232448;                // 227 KB opt-in shared mem
 constexpr int TC_SMEM_HEAD = 2048;                   // 1 KB alignment slack + 1 KB of mbarriers / TMEM slot
 constexpr int TC_THREADS = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: epilogue (2 per TMEM lane quadrant)
 constexpr int TC_PAIR_DEFAULT = 0; // CTA-pair (cta_group::2) GEMM tiles: opt-in via EVC_TC_PAIR=1 until validated on hardware
+constexpr int TC_SPLIT_PRODUCER_DEFAULT = 0;   // two TMA producer threads per CTA: opt-in via EVC_SPLIT_PRODUCER=1 until measured
 constexpr int TC_K_CHUNK = 32;   // k-blocks (of 64) accumulated in TMEM before promotion to an fp32 add
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -223,7 +224,8 @@ template <int SPLIT_A>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                           const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
-                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int mgroup, int single, int n_stages)
+                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int mgroup, int single, int n_stages,
+                          int split_prod)
 {
     // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
     // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
@@ -264,9 +266,16 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+    if ((warp == 0 || (warp == 3 && split_prod >= 1) || (warp == 2 && split_prod >= 2)) && lane == 0) {
+        // ===== TMA producer(s) =====
+        // One elected thread per producer warp.  split_prod = 1: the loads of a stage are issued by TWO threads in
+        // different warps (warp 0: operand 0 + the lo operand + expect_tx, warp 3: operand 1); split_prod = 2: three
+        // threads (warp 2, idle after the TMEM allocation, takes the lo operand) -- so that the per-k-block issue chain
+        // (barrier wait + expect_tx + 2-3 tensor loads) is not serialised in one thread.
         // SPLIT_A (forward): the coupling matrix (A_hi, A_lo) is re-read by every sequence tile -> evict_last
+        const bool ld0 = warp == 0;
+        const bool ld1 = split_prod >= 1 ? warp == 3 : true;
+        const bool ld2 = !single && (split_prod >= 2 ? warp == 2 : warp == 0);
         const uint64_t keep = l2_policy_evict_last();
         int s = 0;
         uint32_t ph = 0;
@@ -276,15 +285,15 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
             for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait_bounded(&empty[s], ph ^ 1u);
                 unsigned char *st = smem + s * stage_bytes;
-                mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                if (ld0) mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
                 if (SPLIT_A) {
-                    tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
-                    tma_load_2d(st + BYTES0, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
-                    if (!single) tma_load_2d_hint(st + BYTES0 + BYTES1, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                    if (ld0) tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                    if (ld1) tma_load_2d(st + BYTES0, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                    if (ld2) tma_load_2d_hint(st + BYTES0 + BYTES1, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
                 } else {
-                    tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
-                    tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
-                    if (!single) tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                    if (ld0) tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
+                    if (ld1) tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                    if (ld2) tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
                 }
                 if (++s == n_stages) { s = 0; ph ^= 1u; }
             }
@@ -1031,6 +1040,14 @@ int plm_tc_make_maps(const PlmTcGeom &t, void *d_xt, void *d_rt_hi, void *d_rt_l
     return 0;
 }
 
+// 1 = the tensor loads of a stage are issued by two producer threads (warp 0: A, warp 3: B)
+static int split_producer()
+{
+    static int sp_env = -2;
+    const int e = env_int_once("EVC_SPLIT_PRODUCER", &sp_env);
+    return e >= 0 ? e : TC_SPLIT_PRODUCER_DEFAULT;
+}
+
 // 1 = cta_group::2 tiles (256 x 192 per CTA pair), 0 = one CTA per 128 x 192 tile
 static int pair_mode()
 {
@@ -1066,7 +1083,7 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
     const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
                                                                 (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK,
-                                                                m_tiles, single, n_stages);
+                                                                m_tiles, single, n_stages, split_producer());
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -1163,7 +1180,8 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
     const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
     tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
                                                                 num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK,
-                                                                forward_mgroup(t, single, m_tiles), single, n_stages);
+                                                                forward_mgroup(t, single, m_tiles), single, n_stages,
+                                                                split_producer());
     EVC_KERNEL_CHECK();
     return 0;
 }
