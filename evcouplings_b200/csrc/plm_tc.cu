@@ -121,6 +121,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// true on exactly one lane of a fully converged warp (elect.sync): lets ptxas keep the single-thread tcgen05 /
+// TMA instructions on the uniform datapath without the per-instruction "loop over active threads" it emits for
+// code that is merely divergent (lane == 0)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n.reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -220,13 +233,13 @@ __device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, 
     }
 }
 
-template <int SPLIT_A>
+template <int SPLIT_A, int SINGLE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                           const __grid_constant__ CUtensorMap tm2, float *__restrict__ D, int64_t ldd,
-                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int mgroup, int single, int n_stages,
-                          int split_prod)
+                          int m_tiles, int n_tiles, int num_kb, int k_chunk, int mgroup, int n_stages, int split_prod)
 {
+    constexpr int single = SINGLE;      // precision mode 1 (bf16 tiles) is a separate instantiation: no lo operand at all
     // Work item = (tile, K chunk).  The tensor core's fp32 accumulator truncates instead of rounding to
     // nearest, so a long accumulation chain picks up a systematic bias (measured -2.6e-5 relative over
     // 782 k-blocks); accumulating at most k_chunk k-blocks in TMEM and adding the chunk results in the
@@ -234,7 +247,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
     constexpr int BYTES0 = TC_A_BYTES;                              // operand 0: A_hi (fwd) / A (bwd), 128 rows
     constexpr int BYTES1 = TC_B_BYTES;                              // operand 1: B (fwd) / B_hi (bwd), 192 rows
     constexpr int BYTES2 = SPLIT_A ? TC_A_BYTES : TC_B_BYTES;       // operand 2: A_lo (fwd) / B_lo (bwd), optional
-    const int stage_bytes = BYTES0 + BYTES1 + (single ? 0 : BYTES2);
+    constexpr int stage_bytes = BYTES0 + BYTES1 + (SINGLE ? 0 : BYTES2);
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem0 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                                              ~static_cast<uintptr_t>(1023));
@@ -266,16 +279,14 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if ((warp == 0 || (warp == 3 && split_prod >= 1) || (warp == 2 && split_prod >= 2)) && lane == 0) {
-        // ===== TMA producer(s) =====
-        // One elected thread per producer warp.  split_prod = 1: the loads of a stage are issued by TWO threads in
-        // different warps (warp 0: operand 0 + the lo operand + expect_tx, warp 3: operand 1); split_prod = 2: three
-        // threads (warp 2, idle after the TMEM allocation, takes the lo operand) -- so that the per-k-block issue chain
-        // (barrier wait + expect_tx + 2-3 tensor loads) is not serialised in one thread.
-        // SPLIT_A (forward): the coupling matrix (A_hi, A_lo) is re-read by every sequence tile -> evict_last
+    if (warp == 0 || (warp == 3 && split_prod >= 1) || (warp == 2 && split_prod >= 2)) {
+        // ===== TMA producer(s): whole warp in the loop, one elected lane issues =====
+        // split_prod = 1: the loads of a stage are issued from TWO warps (warp 0: operand 0 + the lo operand +
+        // expect_tx, warp 3: operand 1); split_prod = 2: three warps (warp 2, idle after the TMEM allocation, takes the
+        // lo operand).  SPLIT_A (forward): the coupling matrix (A_hi, A_lo) is re-read by every sequence tile -> evict_last
         const bool ld0 = warp == 0;
         const bool ld1 = split_prod >= 1 ? warp == 3 : true;
-        const bool ld2 = !single && (split_prod >= 2 ? warp == 2 : warp == 0);
+        const bool ld2 = !SINGLE && (split_prod >= 2 ? warp == 2 : warp == 0);
         const uint64_t keep = l2_policy_evict_last();
         int s = 0;
         uint32_t ph = 0;
@@ -284,23 +295,29 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
             decode_tile(tile, m_tiles, n_tiles, mgroup, m_tile, n_tile);
             for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait_bounded(&empty[s], ph ^ 1u);
-                unsigned char *st = smem + s * stage_bytes;
-                if (ld0) mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                if (SPLIT_A) {
-                    if (ld0) tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
-                    if (ld1) tma_load_2d(st + BYTES0, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
-                    if (ld2) tma_load_2d_hint(st + BYTES0 + BYTES1, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
-                } else {
-                    if (ld0) tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
-                    if (ld1) tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
-                    if (ld2) tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                if (elect_one()) {
+                    unsigned char *st = smem + s * stage_bytes;
+                    if (ld0) mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    if (SPLIT_A) {
+                        if (ld0) tma_load_2d_hint(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                        if (ld1) tma_load_2d(st + BYTES0, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                        if (ld2) tma_load_2d_hint(st + BYTES0 + BYTES1, &tm1, kb * TC_BK, m_tile * TC_BM, &full[s], keep);
+                    } else {
+                        if (ld0) tma_load_2d(st, &tm0, kb * TC_BK, m_tile * TC_BM, &full[s]);
+                        if (ld1) tma_load_2d(st + BYTES0, &tm1, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                        if (ld2) tma_load_2d(st + BYTES0 + BYTES1, &tm2, kb * TC_BK, n_tile * TC_BN, &full[s]);
+                    }
                 }
+                __syncwarp();
                 if (++s == n_stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp runs the loop (all lanes wait on the barriers, all values are warp-uniform);
+        //       the tcgen05 instructions are issued by the lane elect.sync picks =====
         constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+        const uint64_t desc0 = make_desc_sw128(smem);                 // stage 0, operand 0; everything else is an offset
+        constexpr uint64_t OFF1 = (uint64_t)(BYTES0 >> 4), OFF2 = (uint64_t)((BYTES0 + BYTES1) >> 4);
         int s = 0, wl = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -313,25 +330,26 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait_bounded(&full[s], ph);
                     tc_fence_after();
-                    unsigned char *st = smem + s * stage_bytes;
-                    const uint64_t d0 = make_desc_sw128(st);
-                    const uint64_t d1 = make_desc_sw128(st + BYTES0);
-                    const uint64_t d2 = make_desc_sw128(st + BYTES0 + BYTES1);
+                    if (elect_one()) {
+                        const uint64_t d0 = desc0 + (uint64_t)((s * stage_bytes) >> 4);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
-                        // operand 0 is always the 128-row (A) tile, operand 1 the 192-row (B) tile
-                        umma_bf16(tmem_d, d0 + koff, d1 + koff, idesc, first);
-                        if (!single) {
-                            if (SPLIT_A) umma_bf16(tmem_d, d2 + koff, d1 + koff, idesc, 1u);     // A_lo * B
-                            else umma_bf16(tmem_d, d0 + koff, d2 + koff, idesc, 1u);             // A * B_lo
+                        for (int k = 0; k < TC_BK / 16; k++) {
+                            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                            const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                            // operand 0 is always the 128-row (A) tile, operand 1 the 192-row (B) tile
+                            umma_bf16(tmem_d, d0 + koff, d0 + OFF1 + koff, idesc, first);
+                            if (!SINGLE) {
+                                if (SPLIT_A) umma_bf16(tmem_d, d0 + OFF2 + koff, d0 + OFF1 + koff, idesc, 1u);   // A_lo * B
+                                else umma_bf16(tmem_d, d0 + koff, d0 + OFF2 + koff, idesc, 1u);                   // A * B_lo
+                            }
                         }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
+                    __syncwarp();
                     if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&acc_full[acc]);
+                if (elect_one()) umma_commit(&acc_full[acc]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -1062,8 +1080,6 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
     const int stage = TC_A_BYTES + TC_B_BYTES + (single ? 0 : TC_B_BYTES);
     const int n_stages = stages_for(stage);
     const size_t smem = (size_t)n_stages * stage + TC_SMEM_HEAD;
-    EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TC_SMEM_LIMIT));
     static int kc_env = -2;
     const int kc = env_int_once("EVC_KCHUNK", &kc_env);
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Np / TC_BN);
@@ -1081,9 +1097,17 @@ int plm_tc_backward(const PlmGeom &g, const PlmTcGeom &t, const void *maps, floa
         return 0;
     }
     const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
-    tc_gemm_persistent_kernel<0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
-                                                                (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK,
-                                                                m_tiles, single, n_stages, split_producer());
+    if (single) {
+        EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        tc_gemm_persistent_kernel<0, 1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
+                                                                       (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK, m_tiles,
+                                                                       n_stages, split_producer());
+    } else {
+        EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        tc_gemm_persistent_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_Gd, t.Np, m_tiles, n_tiles,
+                                                                       (int)(t.Kp / TC_BK), kc > 0 ? kc : TC_K_CHUNK, m_tiles,
+                                                                       n_stages, split_producer());
+    }
     EVC_KERNEL_CHECK();
     return 0;
 }
@@ -1159,8 +1183,6 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
     const int stage = TC_A_BYTES + TC_B_BYTES + (single ? 0 : TC_A_BYTES);
     const int n_stages = stages_for(stage);
     const size_t smem = (size_t)n_stages * stage + TC_SMEM_HEAD;
-    EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TC_SMEM_LIMIT));
     const int m_tiles = (int)(t.Mp / TC_BM), n_tiles = (int)(t.Ns / TC_BN);
     const int num_kb = (int)(t.Kw / TC_BK);
     if (pair_mode()) {
@@ -1178,10 +1200,17 @@ int plm_tcf_logits(const PlmGeom &g, const PlmTcfGeom &t, const void *maps, floa
         return 0;
     }
     const int grid = std::min(sm_count_current(), m_tiles * n_tiles);
-    tc_gemm_persistent_kernel<1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles,
-                                                                num_kb, num_kb <= 128 ? num_kb : TC_K_CHUNK,
-                                                                forward_mgroup(t, single, m_tiles), single, n_stages,
-                                                                split_producer());
+    const int kchunk = num_kb <= 128 ? num_kb : TC_K_CHUNK;
+    const int mgroup = forward_mgroup(t, single, m_tiles);
+    if (single) {
+        EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        tc_gemm_persistent_kernel<1, 1><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles, num_kb,
+                                                                       kchunk, mgroup, n_stages, split_producer());
+    } else {
+        EVC_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        tc_gemm_persistent_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(m[0], m[1], m[2], d_zt, t.Ns, m_tiles, n_tiles, num_kb,
+                                                                       kchunk, mgroup, n_stages, split_producer());
+    }
     EVC_KERNEL_CHECK();
     return 0;
 }
