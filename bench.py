@@ -392,9 +392,9 @@ def run_b200(args):
     # real-valued operand); bf16 mode: one.  Gather path / HBM accounting: 8 B per cell-op per evaluation.
     local_cells = float(n_local) * L * L * Q
     lq = float(L * Q)
-    names = ["expand", {"tc": "tc_gemm_persistent_kernel<1> (forward logits)", "tcfused": "tc_fwd_fused_kernel",
+    names = ["expand", {"tc": "tc_gemm_persistent_kernel<1,*> (forward logits)", "tcfused": "tc_fwd_fused_kernel",
                        "gather": "plm_fwd_kernel"}[prob.forward],
-             "plm_softmax_kernel", "tc_gemm_persistent_kernel<0> (backward)" if prob.backward == "tc" else "plm_bwd_kernel",
+             "plm_softmax_kernel", "tc_gemm_persistent_kernel<0,*> (backward)" if prob.backward == "tc" else "plm_bwd_kernel",
              "finalize"]
     dom = 1 if stage_ms[1] >= stage_ms[3] else 3
     dom_is_tc = (prob.forward in ("tc", "tcfused")) if dom == 1 else (prob.backward == "tc")
@@ -549,10 +549,12 @@ def ncu_traffic(kernel_name, precision):
     """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` extract
     (profiles/r2_ncu_traffic.json, written by profiles/summarize_ncu.py from the .ncu-rep of this round)."""
     path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not kernel_name.startswith("tc_gemm_persistent_kernel"):
+        return None, None           # the table holds the default-path GEMMs only
     try:
         with open(path) as f:
             table = json.load(f)
-        key = ("fwd" if "<1>" in kernel_name or "fused" in kernel_name else "bwd") + ("_bf16" if precision == "bf16" else "_fp32")
+        key = ("fwd" if "forward" in kernel_name or "fused" in kernel_name else "bwd") + ("_bf16" if precision == "bf16" else "_fp32")
         ent = table.get(key)
         if ent is None:
             return None, None

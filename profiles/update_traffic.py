@@ -5,6 +5,7 @@ usage: python profiles/update_traffic.py fp32=gpurun_out/r2a/prof_fp32.ncu-rep b
 import csv
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -31,9 +32,10 @@ def main(args):
         for r in rows[2:]:
             name = r[col["Kernel Name"]]
             key = None
-            if "tc_gemm_persistent_kernel<1>" in name or "tc_gemm_persistent_kernel<(int)1>" in name:
+            m = re.search(r"tc_gemm_persistent_kernel<(?:\(int\))?([01])", name)      # <SPLIT_A[, SINGLE]>
+            if m and m.group(1) == "1":
                 key = "fwd_" + prec
-            elif "tc_gemm_persistent_kernel<0>" in name or "tc_gemm_persistent_kernel<(int)0>" in name:
+            elif m and m.group(1) == "0":
                 key = "bwd_" + prec
             elif "plm_softmax_kernel" in name:
                 key = "softmax_" + prec
