@@ -25,13 +25,13 @@ tr $G --steps 100 --no-subrecords > $O/weak_$G.json 2> $O/weak_$G.err; show $O/w
 echo "== strong scaling point N=$G (50k sequences in total, the size the metric is quoted on)"
 tr $G --steps 100 --scaling strong --no-subrecords > $O/strong_$G.json 2> $O/strong_$G.err; show $O/strong_$G.json
 grep -h "NCCL INFO.*\(nranks\|NVLS\|Connected\)" $O/weak_$G.err | head -6
-if [ $G -lt 8 ]; then
-  echo "== bf16 tiles, weak, N=$G"
-  tr $G --steps 100 --precision bf16 --no-subrecords > $O/weak_bf16_$G.json 2> /dev/null; show $O/weak_bf16_$G.json
-fi
+echo "== bf16 tiles, weak, N=$G"
+tr $G --steps 100 --precision bf16 --no-subrecords > $O/weak_bf16_$G.json 2> /dev/null; show $O/weak_bf16_$G.json
 if [ $G -eq 8 ]; then
   echo "== BASELINE configs[3]: N=500,000 L=500 sharded over 8 GPUs, one all-reduce of 220 MB per evaluation"
   tr 8 --seqs 62500 --sites 500 --steps 10 --no-subrecords > $O/cfg4_8.json 2> $O/cfg4_8.err; echo "rc=$?"; show $O/cfg4_8.json
+  echo "== all-reduce time vs message size (transfer vs waiting)"
+  PORT=$((PORT+1)); timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $PORT scripts/nccl_sizes.py > $O/nccl_sizes_8.json 2>/dev/null; tail -1 $O/nccl_sizes_8.json | cut -c1-1500
   echo "== Hamming config 3 on 8 GPUs"
   PORT=$((PORT+1)); timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus 8 --workload hamming --steps 5 > $O/hamming_8.json 2>/dev/null; cut -c1-300 $O/hamming_8.json
   echo "== single-process run_plmc over 8 GPUs (launcher), config-4 alignment written as A2M"
