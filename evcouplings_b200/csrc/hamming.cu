@@ -22,6 +22,10 @@
 
 #include <algorithm>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -268,14 +272,18 @@ struct HammingScratch {
     unsigned long long *count = nullptr;
     unsigned long long cap = 0;
 };
-static HammingScratch g_hs[64];
+// candidate buffers per (device, stream): concurrent reweighting passes on different streams do not share one
+static std::mutex g_hs_mutex;
+static std::map<std::pair<int, cudaStream_t>, HammingScratch> g_hs;
 
-static int hamming_scratch(unsigned long long want, HammingScratch **out)
+static int hamming_scratch(unsigned long long want, cudaStream_t st, HammingScratch **out)
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("hamming: bad device"); return 1; }
-    HammingScratch &h = g_hs[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("hamming: bad device"); return 1; }
+    std::lock_guard<std::mutex> lock(g_hs_mutex);
+    HammingScratch &h = g_hs[std::make_pair(dev, st)];
     if (!h.count && cudaMalloc(&h.count, sizeof(unsigned long long)) != cudaSuccess) {
+        h.count = nullptr;
         set_error("hamming: scratch allocation failed");
         return 1;
     }
@@ -363,7 +371,7 @@ int hamming_count_tiles(const uint32_t *d_planes, int64_t N, int L, int min_iden
         HammingScratch *hs = nullptr;
         unsigned long long want = (unsigned long long)std::min<int64_t>((int64_t)1 << 27, std::max<int64_t>(N * 512, 1 << 20));
         if (env_once("EVC_HAMMING_CAND_CAP", &g_env_cap) > 0) want = (unsigned long long)g_env_cap;   // tests
-        if (hamming_scratch(want, &hs) == 0) {
+        if (hamming_scratch(want, st, &hs) == 0) {
             EVC_CUDA(cudaMemsetAsync(hs->count, 0, sizeof(unsigned long long), st));
             int64_t done = tile_begin;
             while (done < tile_end) {

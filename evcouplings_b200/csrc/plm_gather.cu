@@ -649,7 +649,7 @@ __global__ void add_reg_final_kernel(const double *__restrict__ partial, int nbl
     if (tid == 0) fx[1] = fx[0] + s_red[0];
 }
 
-double *reduction_scratch(int nd);   // vecops.cu
+double *reduction_scratch(int nd, cudaStream_t st);   // vecops.cu (per device and stream)
 
 int plm_finalize_fields_n(const PlmGeom &g, const float *d_gh_part, const double *d_fx_part, float *d_gh,
                           double *d_fx, int ntiles, cudaStream_t st)
@@ -670,7 +670,7 @@ int plm_finalize_fields(const PlmGeom &g, const float *d_gh_part, const double *
 int plm_add_reg(const PlmGeom &g, const float *d_x, float *d_g, double *d_fx, float lambda_h,
                 float lambda_J, cudaStream_t st)
 {
-    double *partial = reduction_scratch(REG_BLOCKS);
+    double *partial = reduction_scratch(REG_BLOCKS, st);
     if (!partial) return 1;
     add_reg_kernel<<<REG_BLOCKS, 256, 0, st>>>(d_x, d_g, g.n_params, (int64_t)g.L * g.q, lambda_h,
                                                lambda_J, partial);

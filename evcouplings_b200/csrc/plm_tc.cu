@@ -517,8 +517,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer (both CTAs): own 128 rows of A, own 96-row half of B; bytes land on the leader's barrier =====
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own 96-row half of B; bytes land on the leader's barrier;
+        //       whole warp in the loop, one elected lane issues =====
         const uint64_t keep = l2_policy_evict_last();
         int s = 0;
         uint32_t ph = 0;
@@ -529,23 +530,28 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const int row_b = n_tile * TC_BN + (int)rank * TC_BN_HALF;
             for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait_bounded(&empty[s], ph ^ 1u);
-                unsigned char *st = smem + s * stage_bytes;
-                if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));
-                if (SPLIT_A) {
-                    tma_load_2d_pair_hint(st, &tmA0, kb * TC_BK, row_a, &full[s], keep);
-                    tma_load_2d_pair(st + TC_A_BYTES, &tmB0, kb * TC_BK, row_b, &full[s]);
-                    if (!single) tma_load_2d_pair_hint(st + TC_A_BYTES + TC_BH_BYTES, &tmA1, kb * TC_BK, row_a, &full[s], keep);
-                } else {
-                    tma_load_2d_pair(st, &tmA0, kb * TC_BK, row_a, &full[s]);
-                    tma_load_2d_pair(st + TC_A_BYTES, &tmB0, kb * TC_BK, row_b, &full[s]);
-                    if (!single) tma_load_2d_pair(st + TC_A_BYTES + TC_BH_BYTES, &tmB1, kb * TC_BK, row_b, &full[s]);
+                if (elect_one()) {
+                    unsigned char *st = smem + s * stage_bytes;
+                    if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));
+                    if (SPLIT_A) {
+                        tma_load_2d_pair_hint(st, &tmA0, kb * TC_BK, row_a, &full[s], keep);
+                        tma_load_2d_pair(st + TC_A_BYTES, &tmB0, kb * TC_BK, row_b, &full[s]);
+                        if (!single) tma_load_2d_pair_hint(st + TC_A_BYTES + TC_BH_BYTES, &tmA1, kb * TC_BK, row_a, &full[s], keep);
+                    } else {
+                        tma_load_2d_pair(st, &tmA0, kb * TC_BK, row_a, &full[s]);
+                        tma_load_2d_pair(st + TC_A_BYTES, &tmB0, kb * TC_BK, row_b, &full[s]);
+                        if (!single) tma_load_2d_pair(st + TC_A_BYTES + TC_BH_BYTES, &tmB1, kb * TC_BK, row_b, &full[s]);
+                    }
                 }
+                __syncwarp();
                 if (++s == n_stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ===== MMA issuer (leader CTA only): M = 256 across the pair =====
+    } else if (warp == 1 && leader) {
+        // ===== MMA issuer (leader CTA only): M = 256 across the pair; converged warp, elected lane issues =====
         constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BM, TC_BN);
+        const uint64_t desc0 = make_desc_sw128(smem);
+        constexpr uint64_t OFF1 = (uint64_t)(TC_A_BYTES >> 4), OFF2 = (uint64_t)((TC_A_BYTES + TC_BH_BYTES) >> 4);
         int s = 0, wl = 0;
         uint32_t ph = 0;
         for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
@@ -558,24 +564,25 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait_bounded(&full[s], ph);
                     tc_fence_after();
-                    unsigned char *st = smem + s * stage_bytes;
-                    const uint64_t d0 = make_desc_sw128(st);
-                    const uint64_t d1 = make_desc_sw128(st + TC_A_BYTES);
-                    const uint64_t d2 = make_desc_sw128(st + TC_A_BYTES + TC_BH_BYTES);
+                    if (elect_one()) {
+                        const uint64_t d0 = desc0 + (uint64_t)((s * stage_bytes) >> 4);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
-                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
-                        umma_bf16_pair(tmem_d, d0 + koff, d1 + koff, idesc, first);
-                        if (!single) {
-                            if (SPLIT_A) umma_bf16_pair(tmem_d, d2 + koff, d1 + koff, idesc, 1u);     // A_lo * B
-                            else umma_bf16_pair(tmem_d, d0 + koff, d2 + koff, idesc, 1u);             // A * B_lo
+                        for (int k = 0; k < TC_BK / 16; k++) {
+                            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                            const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                            umma_bf16_pair(tmem_d, d0 + koff, d0 + OFF1 + koff, idesc, first);
+                            if (!single) {
+                                if (SPLIT_A) umma_bf16_pair(tmem_d, d0 + OFF2 + koff, d0 + OFF1 + koff, idesc, 1u);     // A_lo * B
+                                else umma_bf16_pair(tmem_d, d0 + koff, d0 + OFF2 + koff, idesc, 1u);                     // A * B_lo
+                            }
                         }
+                        umma_commit_pair(&empty[s]);
                     }
-                    umma_commit_pair(&empty[s]);
+                    __syncwarp();
                     if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit_pair(&acc_full[acc]);
+                if (elect_one()) umma_commit_pair(&acc_full[acc]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

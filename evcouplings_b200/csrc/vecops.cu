@@ -4,6 +4,10 @@
 // on the device in double, so a direction costs no host round trip.  All reductions use a fixed grid
 // and a fixed summation tree => bit-identical on every rank of a data-parallel run.
 // These kernels are HBM-streaming: (4m+6)*n*4 bytes per iteration.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -12,26 +16,30 @@ namespace evc {
 constexpr int RED_BLOCKS = 1024;
 constexpr int RED_THREADS = 256;
 
-static double *g_scratch[64] = {nullptr};
+// Reduction partials are kept per (device, stream): two problems / threads / streams on one device no longer share
+// a buffer.  Buffers live for the lifetime of the process (a few KB each).
+static std::mutex g_scratch_mutex;
+static std::map<std::pair<int, cudaStream_t>, double *> g_scratch;
 
-double *reduction_scratch(int nd)
+double *reduction_scratch(int nd, cudaStream_t st)
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
         set_error("reduction_scratch: bad device");
         return nullptr;
-    }
-    if (!g_scratch[dev]) {
-        if (cudaMalloc(&g_scratch[dev], 4 * RED_BLOCKS * sizeof(double)) != cudaSuccess) {
-            set_error("reduction_scratch: cudaMalloc failed");
-            return nullptr;
-        }
     }
     if (nd > 4 * RED_BLOCKS) {
         set_error("reduction_scratch: request too large");
         return nullptr;
     }
-    return g_scratch[dev];
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    double *&slot = g_scratch[std::make_pair(dev, st)];
+    if (!slot && cudaMalloc(&slot, 4 * RED_BLOCKS * sizeof(double)) != cudaSuccess) {
+        slot = nullptr;
+        set_error("reduction_scratch: cudaMalloc failed");
+        return nullptr;
+    }
+    return slot;
 }
 
 __device__ __forceinline__ double block_sum(double v, double *s_red)
@@ -83,7 +91,7 @@ __global__ void reduce_final_kernel(const double *__restrict__ partial, int nblo
 static int dot_mode(const float *a, const float *b, int64_t n, int mode, const double *den,
                     const double *aux, double *out, cudaStream_t st)
 {
-    double *partial = reduction_scratch(RED_BLOCKS);
+    double *partial = reduction_scratch(RED_BLOCKS, st);
     if (!partial) return 1;
     dot_partial_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial);
     EVC_KERNEL_CHECK();
@@ -203,7 +211,7 @@ __global__ void update_pair_kernel(float *__restrict__ s, float *__restrict__ y,
 int lbfgs_update_pair(float *s, float *y, const float *x, const float *xp, const float *g,
                       const float *gp, double *ys, double *yy, int64_t n, cudaStream_t st)
 {
-    double *partial = reduction_scratch(2 * RED_BLOCKS);
+    double *partial = reduction_scratch(2 * RED_BLOCKS, st);
     if (!partial) return 1;
     update_pair_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(s, y, x, xp, g, gp, n, partial);
     EVC_KERNEL_CHECK();

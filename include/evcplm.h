@@ -19,10 +19,10 @@
  *   - the caller owns all buffers it passes; the library owns what it allocates
  *     inside a handle until evc_plm_destroy.
  *   - a handle is not re-entrant; independent handles may be used from
- *     different processes (one process per GPU for multi-GPU runs).  The evc_vec_*,
- *     evc_lbfgs_*, evc_plm_add_regulariser and evc_hamming_* entry points share a small
- *     per-device reduction / candidate scratch inside the library: use one calling
- *     thread per device for those.
+ *     different threads or processes (one process per GPU for multi-GPU runs).  The
+ *     evc_vec_*, evc_lbfgs_*, evc_plm_add_regulariser and evc_hamming_* entry points keep
+ *     their small reduction / candidate scratch per (device, stream) inside the library:
+ *     concurrent callers must use different streams (or different devices).
  *
  * Parameter vector layout (identical to the plmc_v2 .model file read by
  * evcouplings/couplings/model.py:354-389):
