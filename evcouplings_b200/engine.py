@@ -13,6 +13,7 @@ pass shards the upper-triangular pair tiles and all-reduces the int32 counters.
 """
 import ctypes
 import os
+import time
 
 import numpy as np
 
@@ -358,12 +359,17 @@ class CudaPlmProblem(object):
         errors = []
         views = {}
 
+        stats = {"allreduce_calls": 0, "allreduce_callback_s": 0.0}
+
         def allreduce(user, d_buf, count, stream):
             try:
+                t_cb = time.perf_counter()
                 key = (d_buf, count)
                 if key not in views:
                     views[key] = torch.as_tensor(_DevicePointer(d_buf, count), device=e.device)
                 e.all_reduce(views[key])
+                stats["allreduce_calls"] += 1
+                stats["allreduce_callback_s"] += time.perf_counter() - t_cb      # host time only (the collective is async)
                 return 0
             except BaseException as exc:          # never let an exception cross the C boundary
                 errors.append(exc)
@@ -395,5 +401,6 @@ class CudaPlmProblem(object):
         e.kernel_launches += res.evaluations * (self.launches_per_eval + 2)
         self.fit_seconds = res.seconds
         self.switched_at = res.switched_at
+        self.fit_stats = dict(stats, fit_s=res.seconds, evaluations=res.evaluations, iterations=res.iterations)
         return _lbfgs.LbfgsResult(_lib.LBFGS_STATUS.get(res.status, "LBFGSERR_UNKNOWNERROR"), res.iterations,
                                   res.fx, res.evaluations)

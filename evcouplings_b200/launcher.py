@@ -80,6 +80,12 @@ def run_plmc_multi_gpu(ndev, kwargs, return_run=False, backend="nccl", engine_fa
             log.close()
         raise tools.ExternalToolError("multi-GPU plmc run failed (%s): %s"
                                       % ("timeout" if failed < 0 else "rank %d" % failed, tail))
+    if os.environ.get("EVC_TRACE"):
+        for r, log in enumerate(logs):
+            log.seek(0)
+            for ln in log.read().splitlines():
+                if "evc-trace" in ln:
+                    sys.stderr.write("[rank %d] %s\n" % (r, ln))
     for log in logs:
         log.close()
     with open(result_path, "rb") as f:

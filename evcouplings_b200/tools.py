@@ -134,6 +134,14 @@ class PlmcRun(object):
         self.timings = {}
 
 
+def _trace(msg):
+    """Wall-clock trace of the stages of run_plmc on stderr (EVC_TRACE=1; used to time rank start-up under the launcher)."""
+    if os.environ.get("EVC_TRACE"):
+        import sys
+        sys.stderr.write("[evc-trace %.3f pid %d] %s\n" % (time.time(), os.getpid(), msg))
+        sys.stderr.flush()
+
+
 def _default_engine():
     from .engine import CudaEngine     # raises EngineUnavailableError without library / GPU
     return CudaEngine()
@@ -197,6 +205,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
     """
     run = PlmcRun()
     t_start = time.time()
+    _trace("run_plmc start")
     _make_dirs(couplings_file)
     _require_file("Alignment file does not exist", alignment)
     if param_file is not None:
@@ -222,6 +231,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
         raise ExternalToolError("Could not read alignment {}: {}".format(alignment, e))
     run.alignment = ali
     run.timings["ingest_s"] = time.time() - t_start
+    _trace("ingest done")
     if ali.n_valid < 1:
         raise ExternalToolError("no valid sequences in alignment {}".format(alignment))
     L, q = ali.codes.shape[1], ali.q
@@ -247,6 +257,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
         engine = _default_engine()
     rank = getattr(engine, "rank", 0)
     run.timings["engine_init_s"] = time.time() - t0
+    _trace("engine ready")
 
     # (b) sequence reweighting
     t0 = time.time()
@@ -258,6 +269,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
     n_eff = float(weights.sum())
     run.counts, run.weights, run.n_eff = counts, weights, n_eff
     run.timings["reweighting_s"] = time.time() - t0
+    _trace("reweighting done")
     log.append("Effective number of samples: %.1f\t(%.0f%% identical neighborhood = %.3f samples)"
                % (n_eff, 100.0 * theta, scale))
 
@@ -272,6 +284,7 @@ def run_plmc(alignment, couplings_file, param_file=None,
         fi_counts, fij_counts = problem.weighted_counts()
         fi, fij = model_io.normalise_frequencies(fi_counts, fij_counts, n_eff, ignore_gaps)
         run.timings["frequencies_s"] = time.time() - t0
+        _trace("frequencies done")
         x0 = initial_point(fi, n_eff, L, q)
 
         log.append("\t".join(ITER_FIELDS))
@@ -287,6 +300,9 @@ def run_plmc(alignment, couplings_file, param_file=None,
         res = problem.fit(x0, params, progress)
         run.lbfgs = res
         run.timings["optimisation_s"] = time.time() - t_opt
+        _trace("optimisation done")
+        for key, val in (getattr(problem, "fit_stats", None) or {}).items():
+            run.timings["fit_" + key] = val
         log.append("Gradient optimization: %s" % res.status)
 
         x = problem.get_x()

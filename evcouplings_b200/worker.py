@@ -10,8 +10,11 @@ def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     with open(argv[0]) as f:
         spec = json.load(f)
+    from evcouplings_b200.tools import _trace
+    _trace("worker start")
     import torch
     import torch.distributed as dist
+    _trace("torch imported")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     backend = spec.get("backend") or "nccl"
@@ -20,6 +23,7 @@ def main(argv=None):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     else:
         dist.init_process_group(backend, rank=rank, world_size=world)
+    _trace("process group ready")
     from evcouplings_b200 import tools
     try:
         factory = spec.get("engine_factory")
