@@ -43,6 +43,10 @@ def run_plmc_multi_gpu(ndev, kwargs, return_run=False, backend="nccl", engine_fa
                    MASTER_PORT=str(port))
         env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
         env.pop("EVC_NUM_GPUS", None)
+        # like torchrun: one OpenMP / BLAS thread per rank unless the caller decided otherwise -- ndev ranks each
+        # spinning a full-size host thread pool starve the threads that drive the GPUs
+        for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            env.setdefault(var, "1")
         log = open(os.path.join(workdir, "rank%d.err" % r), "w+")
         logs.append(log)
         procs.append(subprocess.Popen([sys.executable, "-m", "evcouplings_b200.worker", spec_path],
