@@ -2,32 +2,39 @@
 //
 // The north star allows tensor cores for the PLL gradient only if the dense recast beats the gather path under
 // ncu; bench.py / profiles/ carry that comparison (the gather kernels are kept, see plm_gather.cu): forward
-// 5.1 ms -> 2.2 + 0.46 ms, backward 15.7 ms -> 2.2 ms at the same parity tolerance.
+// 5.1 ms -> 2.1 + 0.40 ms, backward 15.7 ms -> 2.2 ms at the same parity tolerance (round 2, config 2).
 //
 // Maths.  With X[n,(j,b)] = [s_nj = b] (one-hot, exact in bf16), the couplings W[(i,a),(j,b)] = J_ij(a,b) and
 // the residuals R[n,(i,a)] = r_ni(a):
 //     forward   Zt[(i,a), n]     = sum_(j,b) W[(i,a),(j,b)] * X[n,(j,b)]          (logits without h)
 //     backward  Gd[(j,b),(i,a)]  = sum_n     X[n,(j,b)]     * R[n,(i,a)]
 //               g_J(i<j)[a][b]   = Gd[(j,b),(i,a)] + Gd[(i,a),(j,b)]
-// The real-valued operand (W or R) is split in two bf16 terms (hi = rn(v), lo = rn(v - hi)): 16 mantissa bits,
-// relative error 2^-17 per term; both products accumulate into the SAME fp32 TMEM accumulator.
+// Precision mode 0 (fp32-equivalent, default): the real-valued operand (W or R) is split in two bf16 terms
+// (hi = rn(v), lo = rn(v - hi)): 16 mantissa bits, relative error 2^-17 per term; both products accumulate into the
+// SAME fp32 TMEM accumulator.  Precision mode 1 ("bf16 tiles", BASELINE configs[4]): hi only, one product per term.
 //
 // Operands, all K-major (TMA 2-D, SWIZZLE_128B):
 //     forward : Wt_hi, Wt_lo [Mp][Kw] bf16 (written by expand_tc every evaluation), X [Xrows][Kw] bf16 (static)
 //     backward: Xt [Mp][Kp] bf16 (static), Rt_hi, Rt_lo [Np][Kp] bf16 (written by plm_softmax_kernel)
 //
-// tc_gemm_persistent_kernel<SPLIT_A>: one persistent CTA per SM, 128 x 192 tiles, K blocks of 64.
-//     warp 0 (1 thread)  TMA producer, 3-stage shared-memory ring, mbarrier expect_tx, L2 evict_last on the
-//                        operand every tile re-reads
-//     warp 1 (1 thread)  MMA issuer: per K block 4 x 2 tcgen05.mma.cta_group::1.kind::f16 (M128 N192 K16) that
-//                        share one operand tile; tcgen05.commit frees the stage / publishes the accumulator
+// tc_gemm_persistent_kernel<SPLIT_A, SINGLE>: one persistent CTA per SM, 128 x 192 tiles, K blocks of 64.
+//     warp 0             TMA producer: shared-memory ring (4 x 56 KB / 3 x 64 KB / 5 x 40 KB depending on mode),
+//                        mbarrier expect_tx, L2 evict_last on the operand every tile re-reads
+//     warp 1             MMA issuer: per K block 4 (x 2 in mode 0) tcgen05.mma.cta_group::1.kind::f16 (M128 N192 K16);
+//                        tcgen05.commit frees the stage / publishes the accumulator
+//                        Both control warps run their loops CONVERGED and issue through elect.sync: as a single
+//                        divergent thread the issue block was ~130 SASS instructions per K block (~700 cycles, more
+//                        than the 384 MMA cycles of a mode-1 K block); now ~25
 //     warp 2             TMEM allocator: 512 columns = two 192-column fp32 accumulators (double buffered)
-//     warps 4..11        epilogue (two per TMEM lane quadrant): tcgen05.ld 32x32b.x32; K-chunk sums are promoted
+//     warps 4..11        epilogue (two per TMEM lane quadrant): tcgen05.ld 32x32b.x16; K-chunk sums are promoted
 //                        into registers with IEEE round-to-nearest adds (the tensor core's own fp32 accumulation
-//                        truncates: measured -2.6e-5 relative bias over 782 K blocks without promotion)
-// Tile order: M tiles in groups of 11, M fastest inside a group (decode_tile) -- see DESIGN.md 4c.
-// Roofline: tensor pipe.  Executed flop per evaluation: 2 GEMMs x 2 products x 2*Mp*Np*Kp = 7.2e12 at N=50k,
-// L=200, q=21; measured 1.60-1.65 PFLOP/s per GEMM = 0.94-0.97 of the cuBLAS bf16 rate on the same part.
+//                        truncates: measured -2.6e-5 relative bias over 782 K blocks without promotion); no spills
+// Tile order: M tiles in groups whose slice of the coupling operand is ~24 MB (L2-resident), M fastest inside a
+// group (decode_tile, forward_mgroup) -- DESIGN.md 4b.
+// tc_gemm_pair_kernel<SPLIT_A>: the same product on CTA pairs (cta_group::2, 256 x 192 tiles); parity-green, slower,
+// opt-in (EVC_TC_PAIR=1) -- DESIGN.md 4b.
+// Roofline: tensor pipe.  Measured (round 2, N=50k, L=200, q=21): mode 0 tensor pipe 90 % / 86-88 % active,
+// 1.5-1.6 PFLOP/s executed per GEMM = 0.89-0.95 of the cuBLAS bf16 burst rate on the same part; mode 1 70 % / 83 %.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
