@@ -75,3 +75,15 @@ def test_compiled_a2m_reader_matches_python_reader(tmp_path):
             msa.read_fasta_matrix(str(q))
         with pytest.raises(msa.AlignmentError, match=msg):
             msa.read_fasta_matrix_py(str(q))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/evcplm.h is the drop-in boundary: it must compile as C (C99, -pedantic), no C++ / torch types."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "evcplm.h"\n'
+                   'int main(void) { evc_fit_params_t p; evc_fit_result_t r; (void)r; evc_fit_default_params(&p);\n'
+                   '  return evc_abi_version() == EVCPLM_ABI_VERSION ? 0 : 1; }\n')
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
