@@ -87,3 +87,32 @@ def test_header_is_plain_c(tmp_path):
     p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
                         "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+
+
+def test_c_program_links_and_calls_the_library(tmp_path):
+    """A plain C host (what a non-Python binding of the reference's plmc call site would be) links against
+    libevcplm.so and uses the device-independent entry points."""
+    import subprocess
+    from evcouplings_b200 import _lib
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "evcplm.h"
+int main(void) {
+    evc_fit_params_t p;
+    evc_fit_default_params(&p);
+    int rc = evc_plm_set_backward(NULL, 1);
+    printf("%d %lld %lld %d %d %s\n", evc_abi_version(), (long long)evc_hamming_num_tiles(300),
+           (long long)evc_hamming_plane_words(300, 40), (int)p.m, rc, evc_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    c = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                        "-levcplm", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert c.returncode == 0, c.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.split(None, 5)
+    assert out[:5] == [str(_lib.ABI_VERSION), "6", "3000", "6", "1"] and "null handle" in out[5]
