@@ -116,3 +116,23 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     out = r.stdout.split(None, 5)
     assert out[:5] == [str(_lib.ABI_VERSION), "6", "3000", "6", "1"] and "null handle" in out[5]
+
+
+def test_shipped_library_is_blackwell_native():
+    """SASS evidence (B200_PROFILING.md "What proves a Blackwell-native kernel"): tcgen05.mma -> UTCHMMA (also the
+    cta_group::2 form), tcgen05.ld -> LDTM, TMA tensor loads -> UTMALDG, bulk copies -> UBLKCP; no legacy HMMA path in
+    the GEMM kernels.  Skipped where cuobjdump is not installed."""
+    import shutil
+    import subprocess
+    import pytest
+    from evcouplings_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UBLKCP", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    gemm = sass[sass.index("tc_gemm_persistent_kernel"):]
+    gemm = gemm[:gemm.index("Function :", 20)] if "Function :" in gemm[20:] else gemm
+    assert "UTCHMMA" in gemm and " HMMA" not in gemm
