@@ -270,3 +270,34 @@ def test_apc_and_frequency_normalisation_properties():
     fi, fij = model_io.normalise_frequencies(np.zeros((3, 20)), np.zeros((3, 20, 20)), 1.0, True)
     assert np.isfinite(fi).all() and np.isfinite(fij).all()
     assert (model_io.apc_cn_scores(np.zeros(3), 3) == 0).all()
+
+
+def test_fx_limb_packing_is_exact_under_fp32_allreduce():
+    """Design invariant behind the single [g, -loglk] collective (csrc/fit.cu fit_pack_fx_kernel / fit_unpack_fx_kernel,
+    restated here in numpy): -loglk is sent as three fixed-point limbs of 18 / 18 / <= 17 bits (resolution 2^-16); any
+    fp32 summation order over up to 64 ranks reproduces the sum of the per-rank values to that resolution, identically
+    on every rank."""
+    rng = np.random.default_rng(0)
+    BITS, SCALE = 18, 65536.0
+    mask = (1 << BITS) - 1
+
+    def pack(v):
+        q = int(np.rint(np.clip(v * SCALE, -9.0e15, 9.0e15)))
+        return np.array([q & mask, (q >> BITS) & mask, q >> (2 * BITS)], dtype=np.float32)      # arithmetic shift keeps the sign
+
+    def unpack(l):
+        q = int(l[0]) + (int(l[1]) << BITS) + int(l[2]) * (1 << (2 * BITS))
+        return q / SCALE
+
+    for world in (1, 2, 8, 64):
+        for scale in (1.0, 1e3, 1e6, 6.5e8, 1.3e11 / world):
+            vals = rng.uniform(-1.0, 1.0, world) * scale
+            vals[0] = abs(vals[0])
+            limbs = np.stack([pack(v) for v in vals])                 # (world, 3) float32
+            exact = sum(int(np.rint(v * SCALE)) for v in vals) / SCALE
+            for order in (np.arange(world), rng.permutation(world), np.arange(world)[::-1]):
+                acc = np.zeros(3, dtype=np.float32)
+                for r in order:                                        # a ring / tree all-reduce is some such order
+                    acc = (acc + limbs[r]).astype(np.float32)
+                assert unpack(acc) == exact, (world, scale)
+            assert abs(exact - vals.sum()) <= world * 0.5 / SCALE + 1e-9 * abs(vals.sum())
